@@ -1,0 +1,142 @@
+/*
+ * flowavenet_b200.h -- C ABI of libflowavenet_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the FloWaveNet flow pass of ryhorv/tf-flowavenet.  The reference has no
+ * FFI of its own: its boundary is the Python class surface of model.py / modules.py, whose
+ * arithmetic runs inside TensorFlow-1.12 kernels.  Each entry point below names the reference
+ * interface (file:line under /root/reference) whose TF op sites it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / TF types.
+ *   - Unless a name ends in _host, every data pointer is a DEVICE pointer owned by the caller.
+ *   - Tensors are channels-last [B, T, C] float32, exactly the reference's layout.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous.
+ *   - Return value: 0 on success, non-zero on error; fwn_last_error() gives a thread-local message.
+ *   - No CPU fallback exists: without a CUDA device every compute entry point fails.
+ */
+#ifndef FLOWAVENET_B200_H_
+#define FLOWAVENET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FWN_ABI_VERSION 1
+
+enum fwn_precision {
+  FWN_FP32 = 0,       /* fp32 storage + fp32 CUDA-core math: the parity mode (1e-4 rel vs oracle)        */
+  FWN_MIXED_BF16 = 1  /* bf16 operands/activations, fp32 accumulate (tcgen05), fp32 flow variables x, log-det */
+};
+
+/* hparams.py:6-50 / hparams8000.py -- only the fields FloWaveNet.__init__ reads (model.py:288-314). */
+typedef struct fwn_config {
+  int32_t n_block;            /* hparams.n_block  (8; 5 for the 8 kHz config)           */
+  int32_t n_flow;             /* hparams.n_flow   (6)                                   */
+  int32_t n_layer;            /* hparams.n_layer  (2) -> dilations 3^n                  */
+  int32_t num_mels;           /* hparams.num_mels (80), must be even                    */
+  int32_t filter_size;        /* hard-coded 256 in Block (model.py:217)                 */
+  int32_t affine;             /* hparams.affine                                         */
+  int32_t causal;             /* hparams.causality                                      */
+  int32_t n_upsample;         /* len(hparams.upsample_scales) <= 4                      */
+  int32_t upsample_scales[4]; /* [16,16] / [8,12]                                       */
+  int32_t gin_channels;       /* <=0: no speaker embedding                              */
+  int32_t n_speakers;
+  int32_t precision;          /* enum fwn_precision                                     */
+} fwn_config;
+
+typedef struct fwn_model* fwn_handle;
+
+const char* fwn_last_error(void);
+int fwn_abi_version(void);
+
+/* ---- model lifetime: replaces FloWaveNet.__init__ (model.py:283-314) + tf.train.Saver restore ---- */
+int fwn_create(const fwn_config* cfg, fwn_handle* out);
+int fwn_destroy(fwn_handle h);
+/* Number of variables the reference graph owns for this config, and the i-th one's name/shape
+ * (names relative to the model scope, e.g. "Block_0/Flow_1/ActNorm/logs"). */
+int fwn_num_params(fwn_handle h);
+int fwn_param_info(fwn_handle h, int index, const char** name, int64_t shape[4], int* rank);
+/* Copy one variable in (device fp32 source) / out (device fp32 destination). */
+int fwn_set_param(fwn_handle h, const char* name, const float* dev_src, int64_t numel, void* stream);
+int fwn_get_param(fwn_handle h, const char* name, float* dev_dst, int64_t numel, void* stream);
+/* Fold weight-norm (convolutional.py:73-83,179-188), absorb squeeze/change_order permutations into
+ * the weights, cast to the compute dtype.  Must be called after the last fwn_set_param. */
+int fwn_prepack(fwn_handle h, void* stream);
+
+/* ---- whole pass ---- */
+int64_t fwn_workspace_bytes(fwn_handle h, int B, int T);
+/* FloWaveNet.forward (model.py:317-347).  x [B,T,1], c [B,T/hop,num_mels], g [B] int32 or NULL.
+ * Writes the two scalars the reference returns; z_out (nullable) receives z as [B,T,1]
+ * (= unsqueeze^n of the reference's internal `out`).  ddi != 0 performs the ActNorm data-dependent
+ * initialisation pass (train.py:221,229 feeding init=True; model.py:30-41) while running. */
+int fwn_forward(fwn_handle h, const float* x, const float* c, const int32_t* g, int B, int T,
+                float* z_out, float* logp_out, float* logdet_out, int ddi,
+                void* workspace, int64_t workspace_bytes, void* stream);
+/* FloWaveNet.reverse (model.py:350-396).  z [B,T,1] -> x_out [B,T,1]. */
+int fwn_reverse(fwn_handle h, const float* z, const float* c, const int32_t* g, int B, int T,
+                float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* Same, with HOST buffers (pinned or pageable): H2D of inputs, pass, D2H of results, synchronous.
+ * This is the call synthesize.py:44-46 (`sess.run(predictions, feed_dict={lc: mel})`) maps to. */
+int fwn_forward_host(fwn_handle h, const float* x, const float* c, const int32_t* g, int B, int T,
+                     float* z_out, float* logp_out, float* logdet_out);
+int fwn_reverse_host(fwn_handle h, const float* z, const float* c, const int32_t* g, int B, int T,
+                     float* x_out);
+/* Time-chunk sharding support: run the pass on rows [t0, t0+Tl) of an utterance of total
+ * length T_total, where the caller supplies z/c for the chunk extended by `halo_l`/`halo_r` samples of
+ * real neighbour data (0 at a true utterance edge).  Only the Tl interior samples are written. */
+int fwn_reverse_chunk(fwn_handle h, const float* z_ext, const float* c_ext, int B, int T_ext, int halo_l,
+                      int halo_r, float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* Number of kernels the last fwn_forward / fwn_reverse on this handle launched (bench.py gpu_launches). */
+int64_t fwn_last_launches(fwn_handle h);
+int fwn_receptive_halo(fwn_handle h); /* samples of halo per side needed for exact chunked synthesis */
+
+/* ---- per-op entry points (reference layout, fp32): one per TF op site of SURVEY 2.3 ---- */
+/* Block.forward squeeze model.py:226-228: y[b,t,2c+k] = x[b,2t+k,c];  x [B,T,C] -> y [B,T/2,2C] */
+int fwn_squeeze(const float* x, float* y, int B, int T, int C, void* stream);
+/* Block.reverse unsqueeze model.py:260-262: y[b,2t+k,c] = x[b,t,2c+k]; x [B,T,C] -> y [B,2T,C/2] */
+int fwn_unsqueeze(const float* x, float* y, int B, int T, int C, void* stream);
+/* change_order model.py:166-174 on one tensor [rows, C]: y = concat(x[:, C/2:], x[:, :C/2]) */
+int fwn_change_order(const float* x, float* y, int64_t rows, int C, void* stream);
+/* ActNorm.forward model.py:86-94: y=(x+b)*exp(3 logs); *logdet_out = mean_c(3 logs) (device scalar) */
+int fwn_actnorm_fwd(const float* x, const float* b, const float* logs, float* y, float* logdet_out,
+                    int64_t rows, int C, void* stream);
+/* ActNorm.reverse model.py:97-102: y = x*exp(-3 logs) - b */
+int fwn_actnorm_rev(const float* x, const float* b, const float* logs, float* y, int64_t rows, int C,
+                    void* stream);
+/* ActNorm DDI values model.py:55-56,65-70: b=-mean(x), logs=log(1/(sqrt(mean((x+b)^2))+1e-7))/3 */
+int fwn_actnorm_ddi(const float* x, float* b_out, float* logs_out, int64_t rows, int C, void* stream);
+/* AffineCoupling elementwise part model.py:133-141 / 155-161.  x [rows,C], net [rows,C]=(log_s|t)
+ * (affine) or [rows,C/2] (additive).  y=[x_a,(x_b-t)exp(-log_s)], *logdet_out=mean(-log_s)/2. */
+int fwn_affine_fwd(const float* x, const float* net, float* y, float* logdet_out, int64_t rows, int C,
+                   int affine, void* stream);
+int fwn_affine_rev(const float* x, const float* net, float* y, int64_t rows, int C, int affine,
+                   void* stream);
+/* One upsampling stage, model.py:398-404 + convolutional.py:155-201: weight-normed Conv2DTranspose
+ * (kernel (2s,3), strides (s,1), SAME, 1->1 channel) + bias + leaky_relu(0.4).
+ * c_in [B,Tm,mels] -> c_out [B,Tm*s,mels]; kernel [2s,3], g [1], bias [1] raw variables. */
+int fwn_upsample_stage(const float* c_in, const float* kernel, const float* g, const float* bias,
+                       float* c_out, int B, int Tm, int mels, int s, void* stream);
+/* Conv.forward modules.py:24-33 + Conv1D.build convolutional.py:53-109: zero pad, VALID dilated
+ * cross-correlation with the weight-normed kernel (wn_g NULL => no weight norm, as ZeroConv1d),
+ * + bias.  x [B,T,Cin] -> y [B,T,Cout]; kernel [k,Cin,Cout].  relu != 0 fuses tf.nn.relu. */
+int fwn_conv1d(const float* x, const float* kernel, const float* wn_g, const float* bias, float* y,
+               int B, int T, int Cin, int Cout, int ksize, int dilation, int causal, int relu,
+               void* stream);
+/* ZeroConv1d.forward modules.py:51-56: (x.W + b) * exp(3 scale).  x [rows,Cin] -> y [rows,Cout] */
+int fwn_zero_conv1d(const float* x, const float* kernel, const float* bias, const float* scale, float* y,
+                    int64_t rows, int Cin, int Cout, void* stream);
+/* ResBlock gate modules.py:124: y = tanh(f) * sigmoid(g) */
+int fwn_gated_activation(const float* f, const float* g, float* y, int64_t n, void* stream);
+/* ResBlock residual modules.py:128: y = (x + res) * sqrt(0.5) */
+int fwn_residual_scale(const float* x, const float* res, float* y, int64_t n, void* stream);
+/* y = a + b (conditioning add modules.py:117-118; skip add_n modules.py:176), optional relu */
+int fwn_add(const float* a, const float* b, float* y, int64_t n, int relu, void* stream);
+/* mean(0.5(-log 2pi - z^2)) model.py:343 -> device scalar */
+int fwn_log_p(const float* z, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWAVENET_B200_H_ */

@@ -1,0 +1,377 @@
+// Bandwidth-bound flow ops in the reference's own layout ([rows, C] fp32, channels-last).
+// One kernel per TF op site of SURVEY 2.3; all are coalesced grid-stride kernels with 128-bit
+// accesses where the shape allows, warp-shuffle reductions and one atomic per CTA.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fwn {
+
+static inline int ew_grid(int64_t n_items, int threads) {
+  int64_t blocks = cdiv(n_items, threads);
+  int64_t cap = (int64_t)num_sms() * 16;  // multiple of the SM count, enough waves for latency hiding
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------- squeeze / unsqueeze / change_order
+// squeeze: y[b,t,2c+k] = x[b,2t+k,c].  Row t of y occupies the same 2C floats as rows 2t,2t+1 of x,
+// so this is a [2,C]->[C,2] transpose inside each 2C-float group: fully coalesced both ways.
+__global__ void squeeze_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int C, bool inverse) {
+  const int C2 = 2 * C;  // group width; for unsqueeze C is the OUTPUT channel count (= Cin/2)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t grp = i / C2;
+    int r = (int)(i - grp * C2);
+    int src;
+    if (!inverse) {  // out index r = 2c+k  <- in index k*C + c
+      src = (r & 1) * C + (r >> 1);
+    } else {         // out index r = k*C + c <- in index 2c+k
+      int k = r / C, c = r - k * C;
+      src = 2 * c + k;
+    }
+    y[i] = __ldg(x + grp * C2 + src);
+  }
+}
+
+int squeeze(const float* x, float* y, int B, int T, int C, cudaStream_t st) {
+  FWN_CHECK(T % 2 == 0, "squeeze: T=%d must be even (model.py:226)", T);
+  int64_t n = (int64_t)B * T * C;
+  if (n == 0) return 0;
+  squeeze_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C, false);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+int unsqueeze(const float* x, float* y, int B, int T, int C, cudaStream_t st) {
+  FWN_CHECK(C % 2 == 0, "unsqueeze: C=%d must be even (model.py:260)", C);
+  int64_t n = (int64_t)B * T * C;
+  if (n == 0) return 0;
+  squeeze_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C / 2, true);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void change_order_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int C) {
+  const int h = C / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / C;
+    int c = (int)(i - row * C);
+    y[i] = __ldg(x + row * C + (c < h ? c + h : c - h));
+  }
+}
+int change_order(const float* x, float* y, int64_t rows, int C, cudaStream_t st) {
+  FWN_CHECK(C % 2 == 0, "change_order: C=%d must be even", C);
+  int64_t n = rows * C;
+  if (n == 0) return 0;
+  change_order_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- ActNorm
+// y = (x + b) * exp(3 logs)  /  y = x * exp(-3 logs) - b.   float4 path when C % 4 == 0 or 4 % C == 0.
+template <bool REV>
+__global__ void actnorm_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ logs,
+                               float* __restrict__ y, int64_t n, int C) {
+  extern __shared__ float sm[];  // [C] bias, [C] scale
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sm[c] = b[c];
+    sm[C + c] = expf(REV ? -3.f * logs[c] : 3.f * logs[c]);
+  }
+  __syncthreads();
+  const bool vec = ((n & 3) == 0) && ((C % 4 == 0) || (4 % C == 0)) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      int c0 = (int)((i * 4) % C);
+      float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int c = c0 + j;
+        if (c >= C) c -= C * (c / C);
+        pv[j] = REV ? pv[j] * sm[C + c] - sm[c] : (pv[j] + sm[c]) * sm[C + c];
+      }
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      int c = (int)(i % C);
+      float v = __ldg(x + i);
+      y[i] = REV ? v * sm[C + c] - sm[c] : (v + sm[c]) * sm[C + c];
+    }
+  }
+}
+__global__ void actnorm_logdet_kernel(const float* __restrict__ logs, float* out, int C) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += 3.f * logs[c];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s / (float)C;
+}
+int actnorm(const float* x, const float* b, const float* logs, float* y, float* logdet_out, int64_t rows, int C, bool rev,
+            cudaStream_t st) {
+  int64_t n = rows * C;
+  if (n > 0) {
+    int grid = ew_grid(cdiv(n, 4), 256);
+    size_t smem = 2 * (size_t)C * sizeof(float);
+    if (rev) actnorm_kernel<true><<<grid, 256, smem, st>>>(x, b, logs, y, n, C);
+    else actnorm_kernel<false><<<grid, 256, smem, st>>>(x, b, logs, y, n, C);
+    FWN_LAUNCH_CHECK();
+  }
+  if (logdet_out) {
+    actnorm_logdet_kernel<<<1, 256, 0, st>>>(logs, logdet_out, C);
+    FWN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// DDI: two-pass (mean, then centred second moment) with double accumulation, like the reference's
+// reduce_mean of (x+b)^2 (model.py:65 is evaluated on the already centred x).
+__global__ void colsum_kernel(const float* __restrict__ x, const float* __restrict__ shift, double* __restrict__ acc, int64_t rows,
+                              int C, bool square) {
+  __shared__ double part[256];
+  if ((int)blockDim.x >= C) {
+    const int tpr = blockDim.x / C;  // threads sharing one channel, striding over rows
+    const int c = threadIdx.x % C, sub = threadIdx.x / C;
+    double s = 0.0;
+    if (sub < tpr) {
+      const float sh = shift ? shift[c] : 0.f;
+      for (int64_t r = (int64_t)blockIdx.x * tpr + sub; r < rows; r += (int64_t)gridDim.x * tpr) {
+        float v = __ldg(x + r * C + c) + sh;
+        s += square ? (double)v * v : (double)v;
+      }
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+      double t = 0.0;
+      for (int j = 0; j < tpr; ++j) t += part[j * C + threadIdx.x];
+      atomicAdd(acc + threadIdx.x, t);
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float sh = shift ? shift[c] : 0.f;
+      double s = 0.0;
+      for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        float v = __ldg(x + r * C + c) + sh;
+        s += square ? (double)v * v : (double)v;
+      }
+      atomicAdd(acc + c, s);
+    }
+  }
+}
+__global__ void ddi_finish_kernel(const double* acc, float* b_out, float* logs_out, int64_t rows, int C, int phase) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (phase == 0) {
+    b_out[c] = (float)(-acc[c] / (double)rows);
+  } else {
+    double var = acc[C + c] / (double)rows;
+    logs_out[c] = (float)(log(1.0 / (sqrt(var) + 1e-7)) / 3.0);
+  }
+}
+int actnorm_ddi(const float* x, float* b_out, float* logs_out, int64_t rows, int C, double* scratch2C, cudaStream_t st) {
+  FWN_CUDA(cudaMemsetAsync(scratch2C, 0, 2 * (size_t)C * sizeof(double), st));
+  int grid = (int)std::min<int64_t>((int64_t)num_sms() * 4, std::max<int64_t>(1, rows / 8));
+  colsum_kernel<<<grid, 256, 0, st>>>(x, nullptr, scratch2C, rows, C, false);
+  FWN_LAUNCH_CHECK();
+  ddi_finish_kernel<<<(int)cdiv(C, 128), 128, 0, st>>>(scratch2C, b_out, logs_out, rows, C, 0);
+  FWN_LAUNCH_CHECK();
+  colsum_kernel<<<grid, 256, 0, st>>>(x, b_out, scratch2C + C, rows, C, true);
+  FWN_LAUNCH_CHECK();
+  ddi_finish_kernel<<<(int)cdiv(C, 128), 128, 0, st>>>(scratch2C, b_out, logs_out, rows, C, 1);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- affine coupling (elementwise part)
+// x [rows,C], net [rows,NC] with NC = C (affine: log_s | t) or C/2 (additive).
+template <bool REV, bool AFFINE>
+__global__ void affine_kernel(const float* __restrict__ x, const float* __restrict__ net, float* __restrict__ y, double* __restrict__ acc,
+                              int64_t rows, int C) {
+  __shared__ double red[32];
+  const int h = C / 2;
+  const int64_t n = rows * C;
+  double ls = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / C;
+    int c = (int)(i - row * C);
+    float v = __ldg(x + i);
+    if (c >= h) {
+      if (AFFINE) {
+        float log_s = __ldg(net + row * C + (c - h));
+        float t = __ldg(net + row * C + c);
+        if (REV) v = v * expf(log_s) + t;
+        else { v = (v - t) * expf(-log_s); ls += (double)log_s; }
+      } else {
+        float t = __ldg(net + row * h + (c - h));
+        v = REV ? v - t : v + t;
+      }
+    }
+    y[i] = v;
+  }
+  if (!REV && AFFINE && acc) {
+    ls = block_sum(ls, red);
+    if (threadIdx.x == 0) atomicAdd(acc, ls);
+  }
+}
+__global__ void affine_logdet_finish(const double* acc, float* out, double denom) { *out = (float)(-(*acc) / denom / 2.0); }
+
+int affine(const float* x, const float* net, float* y, float* logdet_out, int64_t rows, int C, bool affine_, bool rev, double* scratch,
+           cudaStream_t st) {
+  FWN_CHECK(C % 2 == 0, "affine: C=%d must be even", C);
+  int64_t n = rows * C;
+  if (n == 0) return 0;
+  int grid = ew_grid(n, 256);
+  if (scratch) FWN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  if (affine_) {
+    if (rev) affine_kernel<true, true><<<grid, 256, 0, st>>>(x, net, y, nullptr, rows, C);
+    else affine_kernel<false, true><<<grid, 256, 0, st>>>(x, net, y, scratch, rows, C);
+  } else {
+    if (rev) affine_kernel<true, false><<<grid, 256, 0, st>>>(x, net, y, nullptr, rows, C);
+    else affine_kernel<false, false><<<grid, 256, 0, st>>>(x, net, y, nullptr, rows, C);
+  }
+  FWN_LAUNCH_CHECK();
+  if (!rev && affine_ && logdet_out) {
+    affine_logdet_finish<<<1, 1, 0, st>>>(scratch, logdet_out, (double)rows * (C / 2));
+    FWN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- small elementwise helpers
+__global__ void gated_kernel(const float* __restrict__ f, const float* __restrict__ g, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = tanhf(__ldg(f + i)) * (1.f / (1.f + expf(-__ldg(g + i))));
+}
+__global__ void residual_kernel(const float* __restrict__ x, const float* __restrict__ r, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (__ldg(x + i) + __ldg(r + i)) * 0.70710678118654752440f;
+}
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n, bool relu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = __ldg(a + i) + __ldg(b + i);
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+int gated_activation(const float* f, const float* g, float* y, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  gated_kernel<<<ew_grid(n, 256), 256, 0, st>>>(f, g, y, n);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+int residual_scale(const float* x, const float* r, float* y, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  residual_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, r, y, n);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+int add(const float* a, const float* b, float* y, int64_t n, bool relu, cudaStream_t st) {
+  if (n == 0) return 0;
+  add_kernel<<<ew_grid(n, 256), 256, 0, st>>>(a, b, y, n, relu);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// log_p = mean(0.5 (-log 2pi - z^2))
+__global__ void sumsq_kernel(const float* __restrict__ z, double* __restrict__ acc, int64_t n) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = __ldg(z + i);
+    s += (double)v * v;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+__global__ void logp_finish(const double* acc, float* out, double n) {
+  *out = (float)(0.5 * (-1.8378770664093454835606594728112 - (*acc) / n));
+}
+int sumsq(const float* z, double* acc, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  sumsq_kernel<<<ew_grid(n, 256), 256, 0, st>>>(z, acc, n);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+int log_p(const float* z, float* out, int64_t n, double* scratch, cudaStream_t st) {
+  FWN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  if (sumsq(z, scratch, n, st)) return 1;
+  logp_finish<<<1, 1, 0, st>>>(scratch, out, (double)n);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- upsampler (transposed conv stage)
+// out[b,i,m] = lrelu( bias + sum_{kh in {r, r+s}} sum_{kw} in[b, j(kh), m+kw-1] * w[kh,kw] ),
+// r = (i + s/2) mod s, j(r) = (i + s/2) / s, j(r+s) = j(r) - 1.  6 MAC per output, write-bound.
+// SPLIT: write the two mel halves to separate [B*T, mels/2] planes (the fused path's cond layout).
+template <typename TOut, bool SPLIT>
+__global__ void upsample_kernel(const float* __restrict__ in, const float* __restrict__ w /*[2s,3] weight-normed*/, const float* __restrict__ bias_p,
+                                TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
+  extern __shared__ float sw[];  // [2s*3]
+  for (int i = threadIdx.x; i < 2 * s * 3; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int To = Tm * s;
+  const int64_t n = (int64_t)B * To * mels;
+  const int half = mels / 2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    int m = (int)(idx % mels);
+    int64_t bt = idx / mels;
+    int i = (int)(bt % To);
+    int b = (int)(bt / To);
+    int q = i + s / 2;
+    int r = q % s, j0 = q / s;
+    float acc = __ldg(bias_p);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      int j = j0 - a, kh = r + a * s;
+      if (j < 0 || j >= Tm) continue;
+      const float* row = in + ((int64_t)b * Tm + j) * mels;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int mm = m + 1 - kw;  // in[m'] with m' + kw - 1 = m
+        if (mm >= 0 && mm < mels) acc = fmaf(__ldg(row + mm), sw[kh * 3 + kw], acc);
+      }
+    }
+    acc = fmaxf(acc, 0.4f * acc);
+    if (SPLIT) {
+      if (m < half) out0[bt * half + m] = from_f<TOut>(acc);
+      else out1[bt * half + (m - half)] = from_f<TOut>(acc);
+    } else {
+      out0[idx] = from_f<TOut>(acc);
+    }
+  }
+}
+// weight norm of the [2s,3,1,1] kernel over axes [0,2] => per kw column (convolutional.py:186)
+__global__ void upsample_wn_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int s) {
+  int kw = threadIdx.x;
+  if (kw >= 3) return;
+  float ss = 0.f;
+  for (int kh = 0; kh < 2 * s; ++kh) ss += v[kh * 3 + kw] * v[kh * 3 + kw];
+  float sc = rsqrtf(fmaxf(ss, 1e-12f)) * g[0];
+  for (int kh = 0; kh < 2 * s; ++kh) w[kh * 3 + kw] = v[kh * 3 + kw] * sc;
+}
+int upsample_weight_norm(const float* v, const float* g, float* w, int s, cudaStream_t st) {
+  upsample_wn_kernel<<<1, 32, 0, st>>>(v, g, w, s);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+template <typename TOut>
+int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* out0, TOut* out1, int B, int Tm, int mels, int s, bool split,
+                     cudaStream_t st) {
+  int64_t n = (int64_t)B * Tm * s * mels;
+  if (n == 0) return 0;
+  int grid = ew_grid(n, 256);
+  size_t smem = 2 * (size_t)s * 3 * sizeof(float);
+  if (split) upsample_kernel<TOut, true><<<grid, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+  else upsample_kernel<TOut, false><<<grid, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+int upsample_stage(const float* in, const float* w, const float* bias, void* out0, void* out1, int B, int Tm, int mels, int s, bool split,
+                   bool bf16, cudaStream_t st) {
+  if (bf16) return upsample_stage_t<__nv_bfloat16>(in, w, bias, (__nv_bfloat16*)out0, (__nv_bfloat16*)out1, B, Tm, mels, s, split, st);
+  return upsample_stage_t<float>(in, w, bias, (float*)out0, (float*)out1, B, Tm, mels, s, split, st);
+}
+
+}  // namespace fwn

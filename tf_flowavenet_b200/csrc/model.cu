@@ -1,0 +1,722 @@
+// Model handle, weight prepack, workspace plan and the two whole passes (forward log-likelihood,
+// inverse synthesis) of FloWaveNet (model.py:282-404) on one GPU / one stream.
+//
+// Data layout in HBM:
+//   X      fp32 [B, T]            the flow variable, kept in natural time order for the WHOLE pass.
+//                                 Block i merely views it as [B*T/2^(i+1), 2^(i+1)]: the squeeze
+//                                 (model.py:226-228) is a within-row permutation, and it together with
+//                                 change_order (model.py:166-174) is absorbed into the weights at prepack.
+//   cA,cB  act  [B, T, mels/2]    upsampled conditioning, split in its two mel halves (= the c_a / c_b of
+//                                 AffineCoupling, model.py:125); block i views them as [B*T_i, K_c].
+//   h,o,s,u act [B*T_i, 256]      WaveNet hidden state / gated / skip-sum / final activations.
+// No squeeze, unsqueeze, split, concat or change_order kernel ever runs on the model path.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model.h"
+
+namespace fwn {
+
+// ---------------------------------------------------------------- errors / misc
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+static uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// ---------------------------------------------------------------- parameter schema
+// Names follow the reference's variable scopes (model.py:13,110,178,209,284; modules.py:8,41,65,139;
+// convolutional.py:65-93) with Keras layer scopes in first-call order; verified against a
+// run of the reference's own Python in tests/golden/make_golden.py.
+static void add_param(Model* m, const std::string& name, std::vector<int64_t> shape) {
+  ParamDesc d;
+  d.name = name;
+  d.shape = shape;
+  d.numel = 1;
+  for (auto s : shape) d.numel *= s;
+  d.offset = m->raw_floats;
+  m->raw_floats += (d.numel + 3) & ~int64_t(3);
+  m->index[name] = (int)m->params.size();
+  m->params.push_back(d);
+}
+static void add_conv(Model* m, const std::string& p, int k, int cin, int cout) {
+  add_param(m, p + "/kernel", {k, cin, cout});
+  add_param(m, p + "/wn/g", {cout});
+  add_param(m, p + "/bias", {cout});
+}
+
+int model_create(const fwn_config* cfg, Model** out) {
+  FWN_CHECK(cfg && out, "fwn_create: null argument");
+  FWN_CHECK(cfg->n_block >= 1 && cfg->n_block <= 12, "n_block=%d out of range", cfg->n_block);
+  FWN_CHECK(cfg->n_flow >= 1 && cfg->n_layer >= 1 && cfg->n_layer <= 8, "bad n_flow/n_layer");
+  FWN_CHECK(cfg->num_mels >= 2 && cfg->num_mels % 2 == 0, "num_mels=%d must be even (c is split in halves, model.py:125)", cfg->num_mels);
+  FWN_CHECK(cfg->filter_size >= 16 && cfg->filter_size % 16 == 0, "filter_size=%d must be a multiple of 16", cfg->filter_size);
+  FWN_CHECK(cfg->n_upsample >= 1 && cfg->n_upsample <= 4, "n_upsample out of range");
+  FWN_CHECK(cfg->precision == FWN_FP32 || cfg->precision == FWN_MIXED_BF16, "unknown precision %d", cfg->precision);
+  if (cfg->precision == FWN_MIXED_BF16)
+    FWN_CHECK(cfg->num_mels % 8 == 0 && cfg->filter_size == 256, "mixed precision needs num_mels %% 8 == 0 and filter_size 256 (TMA strides / tile shape)");
+  Model* m = new Model();
+  m->cfg = *cfg;
+  m->hop = 1;
+  for (int i = 0; i < cfg->n_upsample; ++i) {
+    FWN_CHECK(cfg->upsample_scales[i] >= 2 && cfg->upsample_scales[i] % 2 == 0, "upsample scale %d must be even", cfg->upsample_scales[i]);
+    m->hop *= cfg->upsample_scales[i];
+    std::string n = i == 0 ? "conv2d_transpose" : "conv2d_transpose_" + std::to_string(i);
+    add_param(m, n + "/kernel", {2 * cfg->upsample_scales[i], 3, 1, 1});
+    add_param(m, n + "/wn/g", {1});
+    add_param(m, n + "/bias", {1});
+  }
+  const int F = cfg->filter_size;
+  int cx = 1, cc = cfg->num_mels;
+  for (int i = 0; i < cfg->n_block; ++i) {
+    cx *= 2;
+    cc *= 2;
+    const int out_ch = cfg->affine ? cx : cx / 2;
+    for (int j = 0; j < cfg->n_flow; ++j) {
+      std::string pre = "Block_" + std::to_string(i) + "/Flow_" + std::to_string(j);
+      add_param(m, pre + "/ActNorm/b", {1, 1, cx});
+      add_param(m, pre + "/ActNorm/logs", {1, 1, cx});
+      std::string w = pre + "/AffineCoupling/WaveNet";
+      add_conv(m, w + "/Conv_front/conv1d", 3, cx / 2, F);
+      for (int n = 0; n < cfg->n_layer; ++n) {
+        std::string r = w + "/ResBlock_0_" + std::to_string(n);
+        add_conv(m, r + "/Conv_filter/conv1d", 3, F, F);
+        add_conv(m, r + "/Conv_gate/conv1d", 3, F, F);
+        add_conv(m, r + "/conv1d", 1, cc / 2, F);    // _filter_conv_c (modules.py:117)
+        add_conv(m, r + "/conv1d_1", 1, cc / 2, F);  // _gate_conv_c   (modules.py:118)
+        add_conv(m, r + "/conv1d_2", 1, F, F);       // _res_conv      (modules.py:126)
+        add_conv(m, r + "/conv1d_3", 1, F, F);       // _skip_conv     (modules.py:127)
+      }
+      add_conv(m, w + "/Conv_final/conv1d", 1, F, F);
+      add_param(m, w + "/ZeroConv1d/conv1d/kernel", {1, F, out_ch});
+      add_param(m, w + "/ZeroConv1d/conv1d/bias", {out_ch});
+      add_param(m, w + "/ZeroConv1d/scale", {1, 1, out_ch});
+    }
+  }
+  if (cfg->gin_channels > 0) add_param(m, "speaker_embeddings", {cfg->n_speakers, cfg->gin_channels});
+  cudaError_t e = cudaMalloc(&m->raw, (size_t)m->raw_floats * sizeof(float));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%lld B) for parameters failed: %s", (long long)m->raw_floats * 4, cudaGetErrorString(e));
+    delete m;
+    return 1;
+  }
+  cudaMemset(m->raw, 0, (size_t)m->raw_floats * sizeof(float));
+  *out = m;
+  return 0;
+}
+
+void model_destroy(Model* m) {
+  if (!m) return;
+  cudaFree(m->raw);
+  cudaFree(m->pack);
+  cudaFree(m->host_ws);
+  cudaFree(m->host_io);
+  delete m;
+}
+
+// ---------------------------------------------------------------- prepack (host side)
+namespace {
+
+struct Bump {  // bump allocator over a host staging buffer mirrored 1:1 on the device
+  std::vector<char> buf;
+  size_t alloc(size_t bytes) {
+    size_t off = (buf.size() + 255) & ~size_t(255);
+    buf.resize(off + bytes, 0);
+    return off;
+  }
+};
+
+struct HostParams {
+  const Model* m;
+  std::vector<float> raw;
+  const float* p(const std::string& n) const {
+    auto it = m->index.find(n);
+    if (it == m->index.end()) abort();
+    return raw.data() + m->params[it->second].offset;
+  }
+};
+
+// weight-normed kernel [k][cin][cout] -> doubles (convolutional.py:80: v * rsqrt(max(sum_{k,i} v^2, 1e-12)) * g)
+static std::vector<double> wn_kernel(const HostParams& hp, const std::string& pre, int k, int cin, int cout) {
+  const float* v = hp.p(pre + "/kernel");
+  const float* g = hp.p(pre + "/wn/g");
+  std::vector<double> ss(cout, 0.0), w((size_t)k * cin * cout);
+  for (int64_t r = 0; r < (int64_t)k * cin; ++r)
+    for (int o = 0; o < cout; ++o) ss[o] += (double)v[r * cout + o] * v[r * cout + o];
+  for (int o = 0; o < cout; ++o) ss[o] = (double)g[o] / sqrt(std::max(ss[o], 1e-12));
+  for (int64_t r = 0; r < (int64_t)k * cin; ++r)
+    for (int o = 0; o < cout; ++o) w[r * cout + o] = (double)v[r * cout + o] * ss[o];
+  return w;
+}
+
+// Store a [K][N] double matrix either as fp32 [K][N] (fp32 engine) or bf16 [Npad][Kpad] (tcgen05 engine, K-major B operand).
+static size_t store_matrix(Bump& b, const std::vector<double>& w, int K, int N, bool bf16, int* ld_out) {
+  if (!bf16) {
+    size_t off = b.alloc((size_t)K * N * 4);
+    float* d = reinterpret_cast<float*>(b.buf.data() + off);
+    for (size_t i = 0; i < (size_t)K * N; ++i) d[i] = (float)w[i];
+    *ld_out = N;
+    return off;
+  }
+  const int Kpad = (K + 63) / 64 * 64, Npad = (N + 15) / 16 * 16;
+  size_t off = b.alloc((size_t)Kpad * Npad * 2);
+  uint16_t* d = reinterpret_cast<uint16_t*>(b.buf.data() + off);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) d[(size_t)n * Kpad + k] = f2bf((float)w[(size_t)k * N + n]);
+  *ld_out = Kpad;
+  return off;
+}
+static size_t store_floats(Bump& b, const std::vector<double>& v, int pad_to = 0) {
+  size_t n = std::max<size_t>(v.size(), (size_t)pad_to);
+  size_t off = b.alloc(n * 4);
+  float* d = reinterpret_cast<float*>(b.buf.data() + off);
+  for (size_t i = 0; i < v.size(); ++i) d[i] = (float)v[i];
+  return off;
+}
+static size_t store_ints(Bump& b, const std::vector<int>& v) {
+  size_t off = b.alloc(v.size() * 4);
+  memcpy(b.buf.data() + off, v.data(), v.size() * 4);
+  return off;
+}
+
+struct CMap { int m, o; };
+
+}  // namespace
+
+int model_prepack(Model* m, cudaStream_t st) {
+  const fwn_config& c = m->cfg;
+  const int F = c.filter_size, L = c.n_layer, H = c.num_mels / 2;
+  const bool bf16 = c.precision == FWN_MIXED_BF16;
+  HostParams hp;
+  hp.m = m;
+  hp.raw.resize((size_t)m->raw_floats);
+  FWN_CUDA(cudaStreamSynchronize(st));
+  FWN_CUDA(cudaMemcpy(hp.raw.data(), m->raw, (size_t)m->raw_floats * 4, cudaMemcpyDeviceToHost));
+
+  Bump b;
+  struct FlowOff {  // offsets into the staging buffer, turned into device pointers after upload
+    size_t a_off, b_off, off2log, an_b, an_s, an_is, front_w, front_b, final_w, final_b, zero_w, zero_b;
+    std::vector<size_t> gate_w, gate_b, rs_w, rs_b;
+  };
+  std::vector<FlowOff> offs;
+  m->flows.clear();
+  double an_logdet = 0.0;
+
+  // ---- upsampler: fold weight norm over axes [0,2] of [2s,3,1,1] => per kw column (convolutional.py:186)
+  std::vector<size_t> up_w, up_b;
+  for (int i = 0; i < c.n_upsample; ++i) {
+    const int s = c.upsample_scales[i];
+    std::string n = i == 0 ? "conv2d_transpose" : "conv2d_transpose_" + std::to_string(i);
+    const float* v = hp.p(n + "/kernel");
+    const double g = hp.p(n + "/wn/g")[0];
+    std::vector<double> w((size_t)2 * s * 3);
+    for (int kw = 0; kw < 3; ++kw) {
+      double ss = 0;
+      for (int kh = 0; kh < 2 * s; ++kh) ss += (double)v[kh * 3 + kw] * v[kh * 3 + kw];
+      const double sc = g / sqrt(std::max(ss, 1e-12));
+      for (int kh = 0; kh < 2 * s; ++kh) w[kh * 3 + kw] = v[kh * 3 + kw] * sc;
+    }
+    up_w.push_back(store_floats(b, w));
+    up_b.push_back(store_floats(b, {(double)hp.p(n + "/bias")[0]}));
+  }
+
+  // ---- permutation tracking: logical channel -> physical (time-ordered) offset
+  std::vector<int> x_off = {0};
+  std::vector<CMap> c_map(c.num_mels);
+  for (int mm = 0; mm < c.num_mels; ++mm) c_map[mm] = {mm, 0};
+  int cx = 1;
+  for (int i = 0; i < c.n_block; ++i) {
+    // squeeze (model.py:226-233): new channel 2c+k <- (row parity k, old channel c)
+    std::vector<int> nx(2 * x_off.size());
+    for (size_t ch = 0; ch < x_off.size(); ++ch)
+      for (int k = 0; k < 2; ++k) nx[2 * ch + k] = k * cx + x_off[ch];
+    std::vector<CMap> nc(2 * c_map.size());
+    for (size_t ch = 0; ch < c_map.size(); ++ch)
+      for (int k = 0; k < 2; ++k) nc[2 * ch + k] = {c_map[ch].m, k * cx + c_map[ch].o};
+    x_off.swap(nx);
+    c_map.swap(nc);
+    cx *= 2;
+    const int nq = cx / 2, Kc = H * cx;
+    for (int j = 0; j < c.n_flow; ++j) {
+      FlowPack fp;
+      FlowOff fo;
+      fp.Cx = cx;
+      fp.nq = nq;
+      fp.Kc = Kc;
+      std::string pre = "Block_" + std::to_string(i) + "/Flow_" + std::to_string(j);
+      std::string wpre = pre + "/AffineCoupling/WaveNet";
+      // a / b halves in logical order
+      std::vector<int> a_off(x_off.begin(), x_off.begin() + nq), b_off(x_off.begin() + nq, x_off.end());
+      std::vector<int> off2log(cx);
+      for (int l = 0; l < cx; ++l) off2log[x_off[l]] = l;
+      fo.a_off = store_ints(b, a_off);
+      fo.b_off = store_ints(b, b_off);
+      fo.off2log = store_ints(b, off2log);
+      // ActNorm params in physical order
+      const float* ab = hp.p(pre + "/ActNorm/b");
+      const float* al = hp.p(pre + "/ActNorm/logs");
+      std::vector<double> vb(cx), vs(cx), vis(cx);
+      double ld = 0;
+      for (int l = 0; l < cx; ++l) {
+        vb[x_off[l]] = ab[l];
+        vs[x_off[l]] = exp(3.0 * (double)al[l]);
+        vis[x_off[l]] = exp(-3.0 * (double)al[l]);
+        ld += 3.0 * (double)al[l];
+      }
+      an_logdet += ld / cx;
+      fo.an_b = store_floats(b, vb);
+      fo.an_s = store_floats(b, vs);
+      fo.an_is = store_floats(b, vis);
+      fp.raw_b = m->raw + m->params[m->index[pre + "/ActNorm/b"]].offset;
+      fp.raw_logs = m->raw + m->params[m->index[pre + "/ActNorm/logs"]].offset;
+      // conditioning half + K order
+      const int half = c_map[0].m / H;
+      std::vector<int> cpos(Kc);
+      for (int l = 0; l < Kc; ++l) {
+        FWN_CHECK(c_map[l].m / H == half, "internal: c_a is not a whole mel half");
+        cpos[l] = c_map[l].o * H + (c_map[l].m % H);
+      }
+      fp.cond_half = half;
+      // front conv [3][nq][F] (input channel q = logical channel q of x_a)
+      {
+        std::vector<double> w = wn_kernel(hp, wpre + "/Conv_front/conv1d", 3, nq, F);
+        fo.front_w = store_floats(b, w);
+        const float* bb = hp.p(wpre + "/Conv_front/conv1d/bias");
+        fo.front_b = store_floats(b, std::vector<double>(bb, bb + F));
+      }
+      for (int n = 0; n < L; ++n) {
+        std::string r = wpre + "/ResBlock_0_" + std::to_string(n);
+        std::vector<double> wf = wn_kernel(hp, r + "/Conv_filter/conv1d", 3, F, F), wg = wn_kernel(hp, r + "/Conv_gate/conv1d", 3, F, F);
+        std::vector<double> wcf = wn_kernel(hp, r + "/conv1d", 1, Kc, F), wcg = wn_kernel(hp, r + "/conv1d_1", 1, Kc, F);
+        const int Kc16 = (Kc + 15) / 16 * 16;
+        const int Kg = 3 * F + Kc16, Ng = 2 * F;
+        std::vector<double> W((size_t)Kg * Ng, 0.0), B(Ng);
+        for (int k = 0; k < 3 * F; ++k)
+          for (int ch = 0; ch < F; ++ch) {
+            W[(size_t)k * Ng + 2 * ch] = wf[(size_t)k * F + ch];
+            W[(size_t)k * Ng + 2 * ch + 1] = wg[(size_t)k * F + ch];
+          }
+        for (int l = 0; l < Kc; ++l)
+          for (int ch = 0; ch < F; ++ch) {
+            W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch] = wcf[(size_t)l * F + ch];
+            W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch + 1] = wcg[(size_t)l * F + ch];
+          }
+        const float *bf = hp.p(r + "/Conv_filter/conv1d/bias"), *bg = hp.p(r + "/Conv_gate/conv1d/bias");
+        const float *bcf = hp.p(r + "/conv1d/bias"), *bcg = hp.p(r + "/conv1d_1/bias");
+        for (int ch = 0; ch < F; ++ch) {
+          B[2 * ch] = (double)bf[ch] + bcf[ch];
+          B[2 * ch + 1] = (double)bg[ch] + bcg[ch];
+        }
+        int ld;
+        fo.gate_w.push_back(store_matrix(b, W, Kg, Ng, bf16, &ld));
+        fp.gate_ld = ld;
+        fo.gate_b.push_back(store_floats(b, B));
+        // res | skip 1x1 (the last layer's residual output is dead in the reference graph: modules.py:170-176)
+        const bool last = n == L - 1;
+        const int Nr = last ? F : 2 * F;
+        std::vector<double> wr = wn_kernel(hp, r + "/conv1d_2", 1, F, F), ws = wn_kernel(hp, r + "/conv1d_3", 1, F, F);
+        const float *br = hp.p(r + "/conv1d_2/bias"), *bs = hp.p(r + "/conv1d_3/bias");
+        std::vector<double> W2((size_t)F * Nr), B2(Nr);
+        for (int k = 0; k < F; ++k)
+          for (int ch = 0; ch < F; ++ch) {
+            if (!last) {
+              W2[(size_t)k * Nr + ch] = wr[(size_t)k * F + ch];
+              W2[(size_t)k * Nr + F + ch] = ws[(size_t)k * F + ch];
+            } else {
+              W2[(size_t)k * Nr + ch] = ws[(size_t)k * F + ch];
+            }
+          }
+        for (int ch = 0; ch < F; ++ch) {
+          if (!last) { B2[ch] = br[ch]; B2[F + ch] = bs[ch]; }
+          else B2[ch] = bs[ch];
+        }
+        fo.rs_w.push_back(store_matrix(b, W2, F, Nr, bf16, &ld));
+        fp.rs_ld = ld;
+        fo.rs_b.push_back(store_floats(b, B2));
+      }
+      {
+        std::vector<double> w = wn_kernel(hp, wpre + "/Conv_final/conv1d", 1, F, F);
+        int ld;
+        fo.final_w = store_matrix(b, w, F, F, bf16, &ld);
+        fp.final_ld = ld;
+        const float* bb = hp.p(wpre + "/Conv_final/conv1d/bias");
+        fo.final_b = store_floats(b, std::vector<double>(bb, bb + F));
+      }
+      {
+        // ZeroConv1d (modules.py:51-56): (u.W + b) * exp(3 scale); exp folded into W and b.
+        // Columns (2q, 2q+1) = (log_s, t) of the q-th transformed channel.  Additive coupling
+        // (model.py:136-139,157-159) is expressed as log_s = 0, t = -net.
+        const int out_ch = c.affine ? cx : nq;
+        const float* zk = hp.p(wpre + "/ZeroConv1d/conv1d/kernel");
+        const float* zb = hp.p(wpre + "/ZeroConv1d/conv1d/bias");
+        const float* zs = hp.p(wpre + "/ZeroConv1d/scale");
+        const int Nz = 2 * nq;
+        std::vector<double> W((size_t)F * Nz, 0.0), B(Nz, 0.0);
+        for (int q = 0; q < nq; ++q) {
+          if (c.affine) {
+            const double e0 = exp(3.0 * (double)zs[q]), e1 = exp(3.0 * (double)zs[nq + q]);
+            for (int k = 0; k < F; ++k) {
+              W[(size_t)k * Nz + 2 * q] = zk[(size_t)k * out_ch + q] * e0;
+              W[(size_t)k * Nz + 2 * q + 1] = zk[(size_t)k * out_ch + nq + q] * e1;
+            }
+            B[2 * q] = zb[q] * e0;
+            B[2 * q + 1] = zb[nq + q] * e1;
+          } else {
+            const double e0 = exp(3.0 * (double)zs[q]);
+            for (int k = 0; k < F; ++k) W[(size_t)k * Nz + 2 * q + 1] = -(double)zk[(size_t)k * out_ch + q] * e0;
+            B[2 * q + 1] = -(double)zb[q] * e0;
+          }
+        }
+        int ld;
+        fo.zero_w = store_matrix(b, W, F, Nz, bf16, &ld);
+        fp.zero_ld = ld;
+        fo.zero_b = store_floats(b, B, (Nz + 15) / 16 * 16);
+      }
+      m->flows.push_back(fp);
+      offs.push_back(fo);
+      // change_order (model.py:190): swap halves of x and c
+      std::rotate(x_off.begin(), x_off.begin() + nq, x_off.end());
+      std::rotate(c_map.begin(), c_map.begin() + c_map.size() / 2, c_map.end());
+    }
+  }
+  // The reverse pass (model.py:374-396) visits the same (x, c) channel orders iff n_flow is even.
+  m->rev_ok = (c.n_flow % 2 == 0);
+
+  // ---- upload + pointer fix-up
+  size_t scal = b.alloc(8 * sizeof(double));
+  reinterpret_cast<double*>(b.buf.data() + scal)[0] = an_logdet;
+  if (m->pack) FWN_CUDA(cudaFree(m->pack));
+  m->pack = nullptr;
+  FWN_CUDA(cudaMalloc(&m->pack, b.buf.size()));
+  m->pack_bytes = b.buf.size();
+  FWN_CUDA(cudaMemcpy(m->pack, b.buf.data(), b.buf.size(), cudaMemcpyHostToDevice));
+  char* base = m->pack;
+  m->d_an_logdet = reinterpret_cast<double*>(base + scal);
+  for (int i = 0; i < c.n_upsample; ++i) {
+    m->up_w[i] = reinterpret_cast<float*>(base + up_w[i]);
+    m->up_b[i] = reinterpret_cast<float*>(base + up_b[i]);
+  }
+  for (size_t f = 0; f < m->flows.size(); ++f) {
+    FlowPack& fp = m->flows[f];
+    const FlowOff& fo = offs[f];
+    fp.a_off = reinterpret_cast<int*>(base + fo.a_off);
+    fp.b_off = reinterpret_cast<int*>(base + fo.b_off);
+    fp.off2log = reinterpret_cast<int*>(base + fo.off2log);
+    fp.an_b = reinterpret_cast<float*>(base + fo.an_b);
+    fp.an_s = reinterpret_cast<float*>(base + fo.an_s);
+    fp.an_is = reinterpret_cast<float*>(base + fo.an_is);
+    fp.front_w = reinterpret_cast<float*>(base + fo.front_w);
+    fp.front_b = reinterpret_cast<float*>(base + fo.front_b);
+    fp.final_w = base + fo.final_w;
+    fp.final_b = reinterpret_cast<float*>(base + fo.final_b);
+    fp.zero_w = base + fo.zero_w;
+    fp.zero_b = reinterpret_cast<float*>(base + fo.zero_b);
+    for (int n = 0; n < L; ++n) {
+      fp.gate_w[n] = base + fo.gate_w[n];
+      fp.gate_b[n] = reinterpret_cast<float*>(base + fo.gate_b[n]);
+      fp.rs_w[n] = base + fo.rs_w[n];
+      fp.rs_b[n] = reinterpret_cast<float*>(base + fo.rs_b[n]);
+    }
+  }
+  m->packed = true;
+  m->plan_B = m->plan_T = -1;  // tensor maps (tcgen05 engine) must be rebuilt
+  return 0;
+}
+
+// ---------------------------------------------------------------- workspace plan
+static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int model_plan(const Model* m, int B, int T, Workspace* w, char* base) {
+  const fwn_config& c = m->cfg;
+  FWN_CHECK(B > 0 && T > 0, "empty input: B=%d T=%d", B, T);
+  FWN_CHECK(T % m->hop == 0, "T=%d is not a multiple of the hop size %d (upsample_scales product; tfrecord.py:53)", T, m->hop);
+  FWN_CHECK(T % (1 << c.n_block) == 0, "T=%d is not a multiple of 2^n_block=%d (squeeze, model.py:226)", T, 1 << c.n_block);
+  const size_t as = c.precision == FWN_MIXED_BF16 ? 2 : 4;
+  const int F = c.filter_size, H = c.num_mels / 2;
+  const size_t M0 = (size_t)B * T / 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = al256(off + bytes);
+    return base ? base + o : (char*)nullptr;
+  };
+  w->sums = (double*)take(8 * sizeof(double));
+  w->ddi = (double*)take(2 * 4096 * sizeof(double));
+  w->x = (float*)take((size_t)B * T * 4);
+  const int s_last = c.upsample_scales[c.n_upsample - 1];
+  const size_t up_elems = c.n_upsample > 1 ? (size_t)B * (T / s_last) * c.num_mels : 0;
+  w->up[0] = (float*)take(up_elems * 4);
+  w->up[1] = (float*)take(c.n_upsample > 2 ? up_elems * 4 : 0);
+  w->cA = take((size_t)B * T * H * as);
+  w->cB = take((size_t)B * T * H * as);
+  w->h0 = take(M0 * F * as);
+  w->h1 = take(M0 * F * as);
+  w->o = take(M0 * F * as);
+  w->s = take(M0 * F * as);
+  w->u = take(M0 * F * as);
+  w->bytes = off;
+  return 0;
+}
+
+// ---------------------------------------------------------------- passes
+__global__ void ddi_phys_finish_kernel(const double* acc, int64_t rows, int Cx, int phase, float* an_b, float* an_s, float* an_is,
+                                       float* raw_b, float* raw_logs, const int* off2log, double* an_logdet) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= Cx) return;
+  const int l = off2log[o];
+  if (phase == 0) {
+    float b = (float)(-acc[o] / (double)rows);
+    an_b[o] = b;
+    raw_b[l] = b;
+  } else {
+    double var = acc[Cx + o] / (double)rows;
+    float logs = (float)(log(1.0 / (sqrt(var) + 1e-7)) / 3.0);   // model.py:69
+    raw_logs[l] = logs;
+    an_s[o] = (float)exp(3.0 * (double)logs);
+    an_is[o] = (float)exp(-3.0 * (double)logs);
+    atomicAdd(an_logdet, 3.0 * (double)logs / Cx);
+  }
+}
+__global__ void colsum_phys_kernel(const float* __restrict__ x, const float* __restrict__ shift, double* __restrict__ acc, int64_t n, int Cx,
+                                   bool square) {
+  // Cx is a power of two <= 4096; each thread owns offset (tid % Cx) when blockDim % Cx == 0, else strides
+  extern __shared__ double part[];
+  const int nth = blockDim.x;
+  if (Cx <= nth) {
+    const int o = threadIdx.x % Cx;
+    const float sh = shift ? shift[o] : 0.f;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * nth + threadIdx.x; i < n; i += (int64_t)gridDim.x * nth) {
+      float v = __ldg(x + i) + sh;
+      s += square ? (double)v * v : (double)v;
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if ((int)threadIdx.x < Cx) {
+      double t = 0.0;
+      for (int j = threadIdx.x; j < nth; j += Cx) t += part[j];
+      atomicAdd(acc + threadIdx.x, t);
+    }
+  } else {
+    for (int o = threadIdx.x; o < Cx; o += nth) {
+      const float sh = shift ? shift[o] : 0.f;
+      double s = 0.0;
+      for (int64_t r = blockIdx.x; r * Cx < n; r += gridDim.x) {
+        float v = __ldg(x + r * Cx + o) + sh;
+        s += square ? (double)v * v : (double)v;
+      }
+      atomicAdd(acc + o, s);
+    }
+  }
+}
+static int ddi_flow(const Model* m, const FlowPack& fp, float* X, int64_t rows, double* scratch, cudaStream_t st) {
+  const int Cx = fp.Cx;
+  FWN_CHECK(Cx <= 4096, "DDI: Cx too large");
+  const int64_t n = rows * Cx;
+  FWN_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)Cx * sizeof(double), st));
+  int grid = (int)std::min<int64_t>((int64_t)num_sms() * 4, std::max<int64_t>(1, n / 1024));
+  colsum_phys_kernel<<<grid, 256, 256 * sizeof(double), st>>>(X, nullptr, scratch, n, Cx, false);
+  FWN_LAUNCH_CHECK();
+  ddi_phys_finish_kernel<<<(int)cdiv(Cx, 128), 128, 0, st>>>(scratch, rows, Cx, 0, fp.an_b, fp.an_s, fp.an_is, fp.raw_b, fp.raw_logs,
+                                                            fp.off2log, m->d_an_logdet);
+  FWN_LAUNCH_CHECK();
+  colsum_phys_kernel<<<grid, 256, 256 * sizeof(double), st>>>(X, fp.an_b, scratch + Cx, n, Cx, true);
+  FWN_LAUNCH_CHECK();
+  ddi_phys_finish_kernel<<<(int)cdiv(Cx, 128), 128, 0, st>>>(scratch, rows, Cx, 1, fp.an_b, fp.an_s, fp.an_is, fp.raw_b, fp.raw_logs,
+                                                            fp.off2log, m->d_an_logdet);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void finish_forward_kernel(const double* sums, const double* an_logdet, float* logp_out, float* logdet_out, double n) {
+  // log_p = mean(0.5(-log 2pi - z^2)) (model.py:343); logdet = sum_flows [mean_c(3 logs) + mean(-log_s)/2] (model.py:80,135,342)
+  if (logp_out) *logp_out = (float)(0.5 * (-1.8378770664093454835606594728112 - sums[1] / n));
+  if (logdet_out) *logdet_out = (float)(*an_logdet - sums[0] / n);
+}
+
+static int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st) {
+  const fwn_config& c = m->cfg;
+  const bool bf16 = c.precision == FWN_MIXED_BF16;
+  int Tm = T / m->hop;
+  const float* in = c_in;
+  for (int i = 0; i < c.n_upsample; ++i) {
+    const int s = c.upsample_scales[i];
+    const bool last = i == c.n_upsample - 1;
+    if (last) {
+      if (upsample_stage(in, m->up_w[i], m->up_b[i], w.cA, w.cB, B, Tm, c.num_mels, s, true, bf16, st)) return 1;
+    } else {
+      float* out = w.up[i & 1];
+      if (upsample_stage(in, m->up_w[i], m->up_b[i], out, nullptr, B, Tm, c.num_mels, s, false, false, st)) return 1;
+      in = out;
+    }
+    Tm *= s;
+  }
+  return 0;
+}
+
+// One coupling WaveNet + the in-place flow update of X (ActNorm + AffineCoupling [+ change_order absorbed]).
+static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, int B, int Ti, bool reverse, cudaStream_t st) {
+  const fwn_config& c = m->cfg;
+  const int F = c.filter_size, L = c.n_layer;
+  const bool bf16 = c.precision == FWN_MIXED_BF16;
+  auto shift_of = [&](int k, int d) { return c.causal ? (k - 2) * d : (k - 1) * d; };  // modules.py:12-15,27
+
+  FrontArgs fa;
+  fa.X = X; fa.Cx = fp.Cx; fa.nq = fp.nq; fa.a_off = fp.a_off;
+  fa.an_b = reverse ? nullptr : fp.an_b;
+  fa.an_s = reverse ? nullptr : fp.an_s;
+  fa.W = fp.front_w; fa.bias = fp.front_b; fa.H = w.h0; fa.B = B; fa.Ti = Ti; fa.F = F;
+  for (int k = 0; k < 3; ++k) fa.shift[k] = shift_of(k, 1);
+  if (front_conv(fa, bf16, st)) return 1;
+
+  void* hin = w.h0;
+  void* hout = w.h1;
+  const void* cond = fp.cond_half == 0 ? w.cA : w.cB;
+  int d = 1;
+  for (int n = 0; n < L; ++n, d *= 3) {
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    for (int k = 0; k < 3; ++k) g.seg[k] = Seg{hin, F, shift_of(k, d), F, k * F};
+    g.seg[3] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
+    g.nseg = 4;
+    g.W = fp.gate_w[n]; g.ldw = fp.gate_ld; g.N = 2 * F;
+    g.e.bias = fp.gate_b[n]; g.e.out0 = w.o; g.e.F = F;
+    if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
+
+    const bool last = n == L - 1;
+    GemmArgs r = {};
+    r.B = B; r.Ti = Ti;
+    r.seg[0] = Seg{w.o, F, 0, F, 0};
+    r.nseg = 1;
+    r.W = fp.rs_w[n]; r.ldw = fp.rs_ld; r.N = last ? F : 2 * F;
+    r.e.bias = fp.rs_b[n]; r.e.F = F; r.e.has_res = !last; r.e.relu = last;
+    r.e.in0 = hin; r.e.out0 = hout; r.e.in1 = n > 0 ? w.s : nullptr; r.e.out1 = w.s;
+    if (run_gemm(m, r, EPI_RES_SKIP, GEMM_RS0 + n, fp, st)) return 1;
+    std::swap(hin, hout);
+  }
+  {
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    g.seg[0] = Seg{w.s, F, 0, F, 0};
+    g.nseg = 1;
+    g.W = fp.final_w; g.ldw = fp.final_ld; g.N = F;
+    g.e.bias = fp.final_b; g.e.out0 = w.u; g.e.ld = F; g.e.relu = 1; g.e.F = F;
+    if (run_gemm(m, g, EPI_PLAIN, GEMM_FINAL, fp, st)) return 1;
+  }
+  {
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    g.seg[0] = Seg{w.u, F, 0, F, 0};
+    g.nseg = 1;
+    g.W = fp.zero_w; g.ldw = fp.zero_ld; g.N = 2 * fp.nq;
+    g.e.bias = fp.zero_b; g.e.F = F;
+    g.e.X = X; g.e.Cx = fp.Cx; g.e.nq = fp.nq; g.e.a_off = fp.a_off; g.e.b_off = fp.b_off;
+    g.e.an_b = fp.an_b; g.e.an_s = reverse ? fp.an_is : fp.an_s;
+    g.e.logdet_acc = reverse ? nullptr : w.sums;
+    g.e.reverse = reverse;
+    if (run_gemm(m, g, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
+  }
+  return 0;
+}
+
+static int check_pass_args(Model* m, const void* x, const void* c, const int32_t* g, int B, int T, void* ws, int64_t ws_bytes,
+                           Workspace* w) {
+  FWN_CHECK(m && m->packed, "model not prepacked: call fwn_prepack after fwn_set_param");
+  FWN_CHECK(x && c, "null input pointer");
+  // model.py:320-321 / 353-354: `if g is None and gin_channels > 0: raise ValueError('g is None')`
+  FWN_CHECK(!(m->cfg.gin_channels > 0 && g == nullptr), "g is None");
+  if (model_plan(m, B, T, w, (char*)ws)) return 1;
+  FWN_CHECK(ws && ws_bytes >= (int64_t)w->bytes, "workspace too small: need %lld bytes, got %lld", (long long)w->bytes, (long long)ws_bytes);
+  return 0;
+}
+
+int model_forward(Model* m, const float* x, const float* c, const int32_t* g, int B, int T, float* z_out, float* logp_out,
+                  float* logdet_out, int ddi, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  Workspace w;
+  if (check_pass_args(m, x, c, g, B, T, ws, ws_bytes, &w)) return 1;
+  if (prepare_engine(m, w, B, T, st)) return 1;
+  float* X = z_out ? z_out : w.x;
+  if (X != x) FWN_CUDA(cudaMemcpyAsync(X, x, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
+  FWN_CUDA(cudaMemsetAsync(w.sums, 0, 8 * sizeof(double), st));
+  if (ddi) FWN_CUDA(cudaMemsetAsync(m->d_an_logdet, 0, sizeof(double), st));
+  if (run_upsample(m, w, c, B, T, st)) return 1;
+  // The speaker embedding g is looked up, tiled and squeezed by the reference (model.py:330-336) but never
+  // reaches a kernel: WaveNet.__call__ drops it (modules.py:188-189).  Outputs do not depend on g.
+  const fwn_config& cf = m->cfg;
+  for (int i = 0; i < cf.n_block; ++i) {
+    const int Ti = T >> (i + 1);
+    for (int j = 0; j < cf.n_flow; ++j) {
+      const FlowPack& fp = m->flows[(size_t)i * cf.n_flow + j];
+      if (ddi && ddi_flow(m, fp, X, (int64_t)B * Ti, w.ddi, st)) return 1;
+      if (run_flow(m, w, fp, X, B, Ti, false, st)) return 1;
+    }
+  }
+  if (sumsq(X, w.sums + 1, (int64_t)B * T, st)) return 1;
+  finish_forward_kernel<<<1, 1, 0, st>>>(w.sums, m->d_an_logdet, logp_out, logdet_out, (double)B * T);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+int model_reverse(Model* m, const float* z, const float* c, const int32_t* g, int B, int T, float* x_out, void* ws, int64_t ws_bytes,
+                  cudaStream_t st) {
+  Workspace w;
+  if (check_pass_args(m, z, c, g, B, T, ws, ws_bytes, &w)) return 1;
+  FWN_CHECK(x_out, "null output pointer");
+  FWN_CHECK(m->rev_ok, "fused reverse needs an even n_flow: with odd n_flow the reference's reverse is not the inverse of forward "
+                       "(change_order parity, model.py:199,359) -- use the per-op Block/Flow API for that case");
+  if (prepare_engine(m, w, B, T, st)) return 1;
+  float* X = x_out;
+  if (X != z) FWN_CUDA(cudaMemcpyAsync(X, z, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
+  if (run_upsample(m, w, c, B, T, st)) return 1;
+  const fwn_config& cf = m->cfg;
+  for (int i = cf.n_block - 1; i >= 0; --i) {
+    const int Ti = T >> (i + 1);
+    for (int j = cf.n_flow - 1; j >= 0; --j)
+      if (run_flow(m, w, m->flows[(size_t)i * cf.n_flow + j], X, B, Ti, true, st)) return 1;
+  }
+  return 0;
+}
+
+int model_receptive_halo(const Model* m) {
+  const fwn_config& c = m->cfg;
+  int rw = 1, d = 1;  // front conv (k=3, d=1) + layers d = 3^n; causal nets look back twice as far
+  for (int n = 0; n < c.n_layer; ++n, d *= 3) rw += d;
+  if (c.causal) rw *= 2;
+  int64_t halo = 0;
+  for (int i = 0; i < c.n_block; ++i) halo += (int64_t)c.n_flow * rw * (2 << i);
+  halo += m->hop;  // the transposed-conv upsampler sees +-1 input frame per stage
+  int64_t q = std::max(m->hop, 1 << c.n_block);
+  while (q % m->hop || q % (1 << c.n_block)) ++q;
+  return (int)((halo + q - 1) / q * q);
+}
+
+}  // namespace fwn

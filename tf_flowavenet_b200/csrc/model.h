@@ -1,0 +1,92 @@
+// Internal model structures (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/flowavenet_b200.h"
+#include "kernels.h"
+
+namespace fwn {
+
+struct ParamDesc {
+  std::string name;
+  std::vector<int64_t> shape;
+  int64_t numel;
+  int64_t offset;  // floats into Model::raw
+};
+
+constexpr int MAX_LAYERS = 8;
+
+// Prepacked weights of one flow (ActNorm + AffineCoupling/WaveNet), device pointers.
+struct FlowPack {
+  int Cx, nq, Kc, cond_half;
+  int *a_off, *b_off, *off2log;
+  float *an_b, *an_s, *an_is;      // ActNorm bias / exp(3 logs) / exp(-3 logs), physical order
+  float *raw_b, *raw_logs;         // the reference-named variables (updated by DDI)
+  float *front_w, *front_b;
+  void* gate_w[MAX_LAYERS]; float* gate_b[MAX_LAYERS];
+  void* rs_w[MAX_LAYERS];   float* rs_b[MAX_LAYERS];
+  void* final_w; float* final_b;
+  void* zero_w;  float* zero_b;
+  int gate_ld, rs_ld, final_ld, zero_ld;
+};
+
+struct Workspace {
+  double* sums;   // [0] sum log_s, [1] sum z^2
+  double* ddi;
+  float* x;
+  float* up[2];
+  void *cA, *cB, *h0, *h1, *o, *s, *u;
+  size_t bytes;
+};
+
+enum GemmId { GEMM_GATE0 = 0, GEMM_RS0 = MAX_LAYERS, GEMM_FINAL = 2 * MAX_LAYERS, GEMM_ZERO = 2 * MAX_LAYERS + 1, GEMM_IDS = 2 * MAX_LAYERS + 2 };
+
+struct TcPlan;  // tensor maps of the tcgen05 engine (gemm_tc.cu)
+
+struct Model {
+  fwn_config cfg;
+  int hop = 1;
+  std::vector<ParamDesc> params;
+  std::unordered_map<std::string, int> index;
+  float* raw = nullptr;
+  int64_t raw_floats = 0;
+  bool packed = false, rev_ok = false;
+  char* pack = nullptr;
+  size_t pack_bytes = 0;
+  std::vector<FlowPack> flows;
+  float* up_w[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* up_b[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* d_an_logdet = nullptr;
+  // tcgen05 engine state
+  TcPlan* tc = nullptr;
+  int plan_B = -1, plan_T = -1;
+  const void* plan_ws = nullptr;
+  // buffers owned by the *_host entry points
+  void* host_ws = nullptr;
+  int64_t host_ws_bytes = 0;
+  void* host_io = nullptr;
+  int64_t host_io_bytes = 0;
+  int64_t launches = 0;  // kernels launched by the last pass (bench.py's gpu_launches)
+};
+
+int model_create(const fwn_config* cfg, Model** out);
+void model_destroy(Model* m);
+int model_prepack(Model* m, cudaStream_t st);
+int model_plan(const Model* m, int B, int T, Workspace* w, char* base);
+int model_forward(Model* m, const float* x, const float* c, const int32_t* g, int B, int T, float* z_out, float* logp_out,
+                  float* logdet_out, int ddi, void* ws, int64_t ws_bytes, cudaStream_t st);
+int model_reverse(Model* m, const float* z, const float* c, const int32_t* g, int B, int T, float* x_out, void* ws, int64_t ws_bytes,
+                  cudaStream_t st);
+int model_receptive_halo(const Model* m);
+
+// engine dispatch (engine.cu): fp32 -> CUDA-core implicit GEMM, mixed -> tcgen05
+int prepare_engine(Model* m, const Workspace& w, int B, int T, cudaStream_t st);
+int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPack& fp, cudaStream_t st);
+void engine_free(Model* m);
+
+}  // namespace fwn
