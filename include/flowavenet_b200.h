@@ -124,6 +124,10 @@ int fwn_upsample_stage(const float* c_in, const float* kernel, const float* g, c
 int fwn_conv1d(const float* x, const float* kernel, const float* wn_g, const float* bias, float* y,
                int B, int T, int Cin, int Cout, int ksize, int dilation, int causal, int relu,
                void* stream);
+/* Mixed-precision twin of fwn_conv1d on the tcgen05 engine (weight norm already folded): x,y bf16 [B,T,C];
+ * w_packed bf16 [ceil16(Cout)][ceil64(ksize*ceil16(Cin))], K index = tap*ceil16(Cin) + cin; bias fp32. */
+int fwn_conv1d_bf16(const void* x, const void* w_packed, const float* bias, void* y, int B, int T, int Cin,
+                    int Cout, int ksize, int dilation, int causal, int relu, void* stream);
 /* ZeroConv1d.forward modules.py:51-56: (x.W + b) * exp(3 scale).  x [rows,Cin] -> y [rows,Cout] */
 int fwn_zero_conv1d(const float* x, const float* kernel, const float* bias, const float* scale, float* y,
                     int64_t rows, int Cin, int Cout, void* stream);

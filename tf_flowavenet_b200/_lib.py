@@ -50,6 +50,7 @@ SIGNATURES = {
     "fwn_affine_rev": (_i, [_fp, _fp, _fp, _l, _i, _i, _p]),
     "fwn_upsample_stage": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _p]),
     "fwn_conv1d": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "fwn_conv1d_bf16": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fwn_zero_conv1d": (_i, [_fp, _fp, _fp, _fp, _fp, _l, _i, _i, _p]),
     "fwn_gated_activation": (_i, [_fp, _fp, _fp, _l, _p]),
     "fwn_residual_scale": (_i, [_fp, _fp, _fp, _l, _p]),

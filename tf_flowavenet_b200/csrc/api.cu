@@ -7,6 +7,11 @@
 
 using namespace fwn;
 
+namespace fwn {
+int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, int T, int Cin, int Cout, int ksize, int dilation, int causal,
+              int relu, cudaStream_t st);
+}
+
 struct fwn_model {
   Model* m;
 };
@@ -293,6 +298,11 @@ int fwn_conv1d(const float* x, const float* kernel, const float* wn_g, const flo
     g.e.colscale = (const float*)sc.p;
   }
   return simt_gemm(g, EPI_PLAIN, S(stream));
+}
+
+int fwn_conv1d_bf16(const void* x, const void* w_packed, const float* bias, void* y, int B, int T, int Cin, int Cout, int ksize,
+                    int dilation, int causal, int relu, void* stream) {
+  return tc_conv1d(x, w_packed, bias, y, B, T, Cin, Cout, ksize, dilation, causal, relu, S(stream));
 }
 
 int fwn_zero_conv1d(const float* x, const float* kernel, const float* bias, const float* scale, float* y, int64_t rows, int Cin, int Cout,

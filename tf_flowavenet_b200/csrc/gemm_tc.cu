@@ -1,0 +1,620 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine (bf16 operands, fp32 accumulate) -- the throughput mode.
+//
+//   acc[128 rows, BN cols] (TMEM, fp32) = sum over K segments of  A_seg[rows shifted in time, 64-wide K chunk] x W[K chunk, BN]
+//
+// * A operand: activations [B, T_i, C] bf16 in HBM, fetched by TMA through a 3-D tensor map (C, T_i, B) with a
+//   (64, 128, 1) box.  A dilated-conv tap is the same load at time coordinate t0 + (k-1)*d; TMA's out-of-bounds
+//   zero fill IS the tf.pad of modules.py:27 and can never bleed across utterances.
+// * B operand: prepacked weights [N, Kpad] bf16 (K-major), 2-D tensor map, (64, BN) box.
+// * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulator stages, so the
+//   epilogue of tile i overlaps the MMAs of tile i+1.  tcgen05.commit releases shared-memory stages / publishes
+//   accumulators through mbarriers.
+// * Epilogue warps read TMEM with tcgen05.ld (each thread owns one output row) and apply the fused flow op:
+//   tanh*sigmoid gate, residual + skip accumulation, bias+ReLU, or ActNorm + affine coupling + log-det in place on x.
+// Persistent grid (<= one CTA per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-5 epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "model.h"
+
+namespace fwn {
+namespace tc {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_SEG = 4;
+
+struct alignas(64) TcArgs {
+  CUtensorMap mapA[MAX_SEG];
+  CUtensorMap mapB;
+  int shift[MAX_SEG];
+  int nchunk[MAX_SEG];       // 64-wide K chunks in the segment
+  int last_ksteps[MAX_SEG];  // valid 16-wide MMA steps in the segment's last chunk (1..4)
+  int wk0[MAX_SEG];          // first W column (k) of the segment
+  int nseg;
+  int B, Ti, tiles_per_utt, n_tiles, N;
+  EpiArgs e;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BN
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  lo = __low2float(v);
+  hi = __high2float(v);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int BIAS_FLOATS = 512;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + BIAS_FLOATS * 4 + 256;
+};
+
+// ---------------------------------------------------------------- epilogue on 16 accumulator columns of one row
+template <int EPI, int BN>
+__device__ __forceinline__ void epilogue16(const TcArgs& a, const float* sbias, int64_t row, bool row_ok, int n_tile, int c0, const uint32_t* v,
+                                           double& ls_sum) {
+  const EpiArgs& e = a.e;
+  const int col = n_tile * BN + c0;  // global column of v[0]
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + sbias[col + j];
+  if (!row_ok) return;
+  if (EPI == EPI_GATE) {
+    // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124)
+    uint32_t p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float o0 = tanh_fast(acc[4 * j]) * sigmoid_fast(acc[4 * j + 1]);
+      float o1 = tanh_fast(acc[4 * j + 2]) * sigmoid_fast(acc[4 * j + 3]);
+      p[j] = pack_bf16(o0, o1);
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.F + col / 2;
+    *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+  } else if (EPI == EPI_RES_SKIP) {
+    const int F = e.F;
+    if (e.has_res && col < F) {  // h_out = (h_in + res) * sqrt(.5)   (modules.py:128)
+      const uint4* hp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + row * F + col);
+      uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+      const uint32_t hu[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      uint32_t p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float lo, hi;
+        unpack_bf16(hu[j], lo, hi);
+        p[j] = pack_bf16((lo + acc[2 * j]) * 0.70710678118654752440f, (hi + acc[2 * j + 1]) * 0.70710678118654752440f);
+      }
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out0) + row * F + col);
+      op[0] = make_uint4(p[0], p[1], p[2], p[3]);
+      op[1] = make_uint4(p[4], p[5], p[6], p[7]);
+    } else {  // skip (+ running sum, + ReLU on the last layer)   (modules.py:127,176-177)
+      const int c = e.has_res ? col - F : col;
+      if (e.in1) {
+        const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + row * F + c);
+        uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+        const uint32_t su[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float lo, hi;
+          unpack_bf16(su[j], lo, hi);
+          acc[2 * j] += lo;
+          acc[2 * j + 1] += hi;
+        }
+      }
+      uint32_t p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float lo = acc[2 * j], hi = acc[2 * j + 1];
+        if (e.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+        p[j] = pack_bf16(lo, hi);
+      }
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out1) + row * F + c);
+      op[0] = make_uint4(p[0], p[1], p[2], p[3]);
+      op[1] = make_uint4(p[4], p[5], p[6], p[7]);
+    }
+  } else if (EPI == EPI_PLAIN) {
+    uint32_t p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float lo = acc[2 * j], hi = acc[2 * j + 1];
+      if (e.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+      p[j] = pack_bf16(lo, hi);
+    }
+    if (col + 15 < a.N) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col);
+      op[0] = make_uint4(p[0], p[1], p[2], p[3]);
+      op[1] = make_uint4(p[4], p[5], p[6], p[7]);
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col + j < a.N) o[j] = __float2bfloat16_rn(e.relu ? fmaxf(acc[j], 0.f) : acc[j]);
+    }
+  } else if (EPI == EPI_AFFINE) {
+    // (2q, 2q+1) = (log_s, t) of transformed element q; ActNorm + coupling in place on the fp32 flow variable
+    float* xr = e.X + row * e.Cx;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int q = col / 2 + p;
+      if (q >= e.nq) break;
+      const float log_s = acc[2 * p], tt = acc[2 * p + 1];
+      const int oa = __ldg(e.a_off + q), ob = __ldg(e.b_off + q);
+      float xa = xr[oa], xb = xr[ob];
+      if (!e.reverse) {
+        xa = (xa + __ldg(e.an_b + oa)) * __ldg(e.an_s + oa);
+        xb = (xb + __ldg(e.an_b + ob)) * __ldg(e.an_s + ob);
+        xb = (xb - tt) * __expf(-log_s);
+        ls_sum += (double)log_s;
+      } else {
+        xb = xb * __expf(log_s) + tt;
+        xa = xa * __ldg(e.an_s + oa) - __ldg(e.an_b + oa);
+        xb = xb * __ldg(e.an_s + ob) - __ldg(e.an_b + ob);
+      }
+      xr[oa] = xa;
+      xr[ob] = xb;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int EPI, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcArgs a) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* sbias = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + C::BIAS_FLOATS);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = a.B * a.tiles_per_utt * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.nseg; ++s) prefetch_tmap(&a.mapA[s]);
+    prefetch_tmap(&a.mapB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  for (int i = threadIdx.x; i < C::BIAS_FLOATS; i += NUM_THREADS) {
+    const int npad = a.n_tiles * BN;
+    sbias[i] = (i < npad && i < a.N) ? __ldg(a.e.bias + i) : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int ub = m_tile / a.tiles_per_utt;
+        const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
+        for (int s = 0; s < a.nseg; ++s) {
+          for (int ch = 0; ch < a.nchunk[s]; ++ch) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* sa = stage_base + (size_t)stage * C::STAGE_BYTES;
+            mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
+            tma_load_3d(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
+            tma_load_2d(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc<BN>();
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty + as, aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        for (int ch = 0; ch < a.nchunk[s]; ++ch) {
+          mbar_wait(full_bar + stage, phase);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+            const int ksteps = (ch == a.nchunk[s] - 1) ? a.last_ksteps[s] : BK / UMMA_K;
+            for (int k = 0; k < ksteps; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte address units
+              umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
+          }
+          accumulate = 1;
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (lane == 0) umma_commit(tmem_full + as);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const int r = lg * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    double ls_sum = 0.0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+      const int ub = m_tile / a.tiles_per_utt;
+      const int t = (m_tile - ub * a.tiles_per_utt) * BM + r;
+      const bool row_ok = t < a.Ti;
+      const int64_t row = (int64_t)ub * a.Ti + t;
+      mbar_wait(tmem_full + as, aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x16(taddr + c0, v);
+        if (BN > 16) tmem_ld_x16(taddr + c0 + 16, v + 16);
+        tmem_ld_wait();
+        epilogue16<EPI, BN>(a, sbias, row, row_ok, n_tile, c0, v, ls_sum);
+        if (BN > 16) epilogue16<EPI, BN>(a, sbias, row, row_ok, n_tile, c0 + 16, v + 16, ls_sum);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty + as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (EPI == EPI_AFFINE) {
+      if (!a.e.reverse && a.e.logdet_acc) {
+        ls_sum = warp_sum(ls_sum);
+        if (lane == 0 && ls_sum != 0.0) atomicAdd(a.e.logdet_acc, ls_sum);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+// activations [B, Ti, C] bf16 (row stride ld elements) -> 3-D map, box (64, 128, 1), 128B swizzle, zero OOB fill
+int make_act_map(CUtensorMap* map, const void* base, int B, int Ti, int C, int64_t ld) {
+  EncodeFn enc = get_encode();
+  FWN_CHECK(enc, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  FWN_CHECK((ld * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) % 16) == 0, "TMA needs 16-byte aligned rows (ld=%lld)", (long long)ld);
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Ti, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)Ti};
+  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations B=%d Ti=%d C=%d) failed: %d", B, Ti, C, (int)r);
+  return 0;
+}
+// weights [Npad, Kpad] bf16 -> 2-D map, box (64, bn)
+int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
+  EncodeFn enc = get_encode();
+  FWN_CHECK(enc, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)Npad};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+  cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights N=%d K=%d box=%d) failed: %d", Npad, Kpad, bn, (int)r);
+  return 0;
+}
+
+template <int EPI, int BN>
+static int launch(const TcArgs& a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  const int total = a.B * a.tiles_per_utt * a.n_tiles;
+  const int grid = std::min(total, num_sms());
+  tc_gemm_kernel<EPI, BN><<<grid, NUM_THREADS, C::SMEM, st>>>(a);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
+int block_n_for(EpiKind kind, int N) {
+  if (kind != EPI_AFFINE && kind != EPI_PLAIN) return 256;
+  int bn = 16;
+  while (bn < N && bn < 256) bn *= 2;
+  return bn;
+}
+
+int tc_launch(TcArgs& a, EpiKind kind, int bn, cudaStream_t st) {
+  FWN_CHECK(a.n_tiles * bn <= Cfg<256>::BIAS_FLOATS, "tc_gemm: N=%d too wide", a.N);
+  switch (kind) {
+    case EPI_GATE: FWN_CHECK(bn == 256, "gate needs BN=256"); return launch<EPI_GATE, 256>(a, st);
+    case EPI_RES_SKIP: FWN_CHECK(bn == 256, "res/skip needs BN=256"); return launch<EPI_RES_SKIP, 256>(a, st);
+    case EPI_PLAIN:
+      switch (bn) {
+        case 16: return launch<EPI_PLAIN, 16>(a, st);
+        case 32: return launch<EPI_PLAIN, 32>(a, st);
+        case 64: return launch<EPI_PLAIN, 64>(a, st);
+        case 128: return launch<EPI_PLAIN, 128>(a, st);
+        default: return launch<EPI_PLAIN, 256>(a, st);
+      }
+    case EPI_AFFINE:
+      switch (bn) {
+        case 16: return launch<EPI_AFFINE, 16>(a, st);
+        case 32: return launch<EPI_AFFINE, 32>(a, st);
+        case 64: return launch<EPI_AFFINE, 64>(a, st);
+        case 128: return launch<EPI_AFFINE, 128>(a, st);
+        default: return launch<EPI_AFFINE, 256>(a, st);
+      }
+  }
+  return 1;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------- engine glue
+struct TcPlan {
+  Workspace w;
+  // activation maps per block: h0, h1, o, s, u (C = F) and cA, cB (C = Kc)
+  std::vector<CUtensorMap> act;  // [n_block * 7]
+  std::vector<CUtensorMap> wmap; // [n_flows * GEMM_IDS]
+  std::vector<int> wbn;          // BN each weight map was built for
+};
+
+static int act_index(const Workspace& w, const void* p) {
+  if (p == w.h0) return 0;
+  if (p == w.h1) return 1;
+  if (p == w.o) return 2;
+  if (p == w.s) return 3;
+  if (p == w.u) return 4;
+  if (p == w.cA) return 5;
+  if (p == w.cB) return 6;
+  return -1;
+}
+
+int tc_prepare(Model* m, const Workspace& w, int B, int T, cudaStream_t st) {
+  if (m->tc && m->plan_B == B && m->plan_T == T && m->plan_ws == (const void*)w.sums) return 0;
+  const fwn_config& c = m->cfg;
+  const int F = c.filter_size, L = c.n_layer, H = c.num_mels / 2;
+  if (!m->tc) m->tc = new TcPlan();
+  TcPlan* p = m->tc;
+  p->w = w;
+  p->act.assign((size_t)c.n_block * 7, CUtensorMap());
+  p->wmap.assign(m->flows.size() * GEMM_IDS, CUtensorMap());
+  p->wbn.assign(m->flows.size() * GEMM_IDS, 0);
+  for (int i = 0; i < c.n_block; ++i) {
+    const int Ti = T >> (i + 1), Kc = H << (i + 1);
+    void* bufs[7] = {w.h0, w.h1, w.o, w.s, w.u, w.cA, w.cB};
+    for (int k = 0; k < 7; ++k) {
+      const int C = k < 5 ? F : Kc;
+      if (tc::make_act_map(&p->act[(size_t)i * 7 + k], bufs[k], B, Ti, C, C)) return 1;
+    }
+  }
+  for (size_t f = 0; f < m->flows.size(); ++f) {
+    const FlowPack& fp = m->flows[f];
+    auto mk = [&](int id, const void* wptr, int N, int Kpad, EpiKind kind) {
+      const int bn = tc::block_n_for(kind, N);
+      const int Npad = (N + 15) / 16 * 16;
+      p->wbn[f * GEMM_IDS + id] = bn;
+      return tc::make_w_map(&p->wmap[f * GEMM_IDS + id], wptr, Npad, Kpad, std::min(bn, Npad));
+    };
+    for (int n = 0; n < L; ++n) {
+      if (mk(GEMM_GATE0 + n, fp.gate_w[n], 2 * F, fp.gate_ld, EPI_GATE)) return 1;
+      if (mk(GEMM_RS0 + n, fp.rs_w[n], n == L - 1 ? F : 2 * F, fp.rs_ld[n], EPI_RES_SKIP)) return 1;
+    }
+    if (mk(GEMM_FINAL, fp.final_w, F, fp.final_ld, EPI_PLAIN)) return 1;
+    if (mk(GEMM_ZERO, fp.zero_w, 2 * fp.nq, fp.zero_ld, EPI_AFFINE)) return 1;
+  }
+  m->plan_B = B;
+  m->plan_T = T;
+  m->plan_ws = (const void*)w.sums;
+  return 0;
+}
+
+int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPack& fp, cudaStream_t st) {
+  TcPlan* p = m->tc;
+  FWN_CHECK(p, "tcgen05 engine not prepared");
+  const size_t f = (size_t)(&fp - m->flows.data());
+  const int block = (int)(f / m->cfg.n_flow);
+  tc::TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nseg = g.nseg;
+  for (int s = 0; s < g.nseg; ++s) {
+    const int ai = act_index(p->w, g.seg[s].A);
+    FWN_CHECK(ai >= 0, "tc_run: segment %d does not read a planned workspace buffer", s);
+    a.mapA[s] = p->act[(size_t)block * 7 + ai];
+    a.shift[s] = g.seg[s].shift;
+    const int K16 = (g.seg[s].K + 15) / 16 * 16;
+    a.nchunk[s] = (K16 + tc::BK - 1) / tc::BK;
+    a.last_ksteps[s] = (K16 - (a.nchunk[s] - 1) * tc::BK) / tc::UMMA_K;
+    a.wk0[s] = g.seg[s].koff;
+  }
+  a.mapB = p->wmap[f * GEMM_IDS + gemm_id];
+  const int bn = p->wbn[f * GEMM_IDS + gemm_id];
+  a.B = g.B;
+  a.Ti = g.Ti;
+  a.tiles_per_utt = (g.Ti + tc::BM - 1) / tc::BM;
+  a.N = g.N;
+  a.n_tiles = (g.N + bn - 1) / bn;
+  a.e = g.e;
+  return tc::tc_launch(a, kind, bn, st);
+}
+
+// Stand-alone mixed-precision conv (per-op entry fwn_conv1d_bf16): y = [relu](conv(x, w) + bias), bf16 in/out.
+// x [B,T,Cin] bf16, w prepacked [ceil16(Cout)][ceil64(ksize*ceil16(Cin))] bf16 (tap-major K), bias fp32 [Cout].
+int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, int T, int Cin, int Cout, int ksize, int dilation, int causal,
+              int relu, cudaStream_t st) {
+  FWN_CHECK(ksize >= 1 && ksize <= 4 && Cin % 8 == 0 && Cout % 8 == 0, "conv1d_bf16: need ksize<=4 and channel counts that are multiples of 8");
+  tc::TcArgs a;
+  memset(&a, 0, sizeof(a));
+  const int Cin16 = (Cin + 15) / 16 * 16, Kpad = (ksize * Cin16 + 63) / 64 * 64, Npad = (Cout + 15) / 16 * 16;
+  const int bn = tc::block_n_for(EPI_PLAIN, Cout);
+  const int pad = causal ? dilation * (ksize - 1) : dilation * (ksize - 1) / 2;
+  a.nseg = ksize;
+  for (int k = 0; k < ksize; ++k) {
+    if (tc::make_act_map(&a.mapA[k], x, B, T, Cin, Cin)) return 1;
+    a.shift[k] = k * dilation - pad;
+    a.nchunk[k] = (Cin16 + tc::BK - 1) / tc::BK;
+    a.last_ksteps[k] = (Cin16 - (a.nchunk[k] - 1) * tc::BK) / tc::UMMA_K;
+    a.wk0[k] = k * Cin16;
+  }
+  if (tc::make_w_map(&a.mapB, w, Npad, Kpad, std::min(bn, Npad))) return 1;
+  a.B = B; a.Ti = T; a.tiles_per_utt = (T + tc::BM - 1) / tc::BM; a.N = Cout; a.n_tiles = (Cout + bn - 1) / bn;
+  a.e.bias = bias; a.e.out0 = y; a.e.ld = Cout; a.e.relu = relu; a.e.F = Cout;
+  return tc::tc_launch(a, EPI_PLAIN, bn, st);
+}
+
+void tc_free(Model* m) {
+  delete m->tc;
+  m->tc = nullptr;
+}
+
+}  // namespace fwn

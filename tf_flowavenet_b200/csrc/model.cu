@@ -360,7 +360,7 @@ int model_prepack(Model* m, cudaStream_t st) {
           else B2[ch] = bs[ch];
         }
         fo.rs_w.push_back(store_matrix(b, W2, F, Nr, bf16, &ld));
-        fp.rs_ld = ld;
+        fp.rs_ld[n] = ld;
         fo.rs_b.push_back(store_floats(b, B2));
       }
       {
@@ -617,7 +617,7 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     r.B = B; r.Ti = Ti;
     r.seg[0] = Seg{w.o, F, 0, F, 0};
     r.nseg = 1;
-    r.W = fp.rs_w[n]; r.ldw = fp.rs_ld; r.N = last ? F : 2 * F;
+    r.W = fp.rs_w[n]; r.ldw = fp.rs_ld[n]; r.N = last ? F : 2 * F;
     r.e.bias = fp.rs_b[n]; r.e.F = F; r.e.has_res = !last; r.e.relu = last;
     r.e.in0 = hin; r.e.out0 = hout; r.e.in1 = n > 0 ? w.s : nullptr; r.e.out1 = w.s;
     if (run_gemm(m, r, EPI_RES_SKIP, GEMM_RS0 + n, fp, st)) return 1;

@@ -32,7 +32,7 @@ struct FlowPack {
   void* rs_w[MAX_LAYERS];   float* rs_b[MAX_LAYERS];
   void* final_w; float* final_b;
   void* zero_w;  float* zero_b;
-  int gate_ld, rs_ld, final_ld, zero_ld;
+  int gate_ld, rs_ld[MAX_LAYERS], final_ld, zero_ld;
 };
 
 struct Workspace {
