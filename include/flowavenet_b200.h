@@ -90,6 +90,12 @@ int fwn_reverse_chunk(fwn_handle h, const float* z_ext, const float* c_ext, int 
                       int halo_r, float* x_out, void* workspace, int64_t workspace_bytes, void* stream);
 /* Number of kernels the last fwn_forward / fwn_reverse on this handle launched (bench.py gpu_launches). */
 int64_t fwn_last_launches(fwn_handle h);
+/* Optional per-kernel-family timing with CUDA events on the launching stream.  Families (index): 0 front conv,
+ * 1 gate GEMM (dilated conv + cond), 2 res/skip GEMM, 3 final conv, 4 zero-conv + ActNorm/affine, 5 upsampler.
+ * fwn_profile_read sums, since the last read, elapsed ms, launch counts and algorithmic work (FLOPs for 0-4,
+ * bytes for 5) per family, then resets. */
+int fwn_profile_enable(fwn_handle h, int on);
+int fwn_profile_read(fwn_handle h, double ms[8], int64_t launches[8], double work[8]);
 int fwn_receptive_halo(fwn_handle h); /* samples of halo per side needed for exact chunked synthesis */
 
 /* ---- per-op entry points (reference layout, fp32): one per TF op site of SURVEY 2.3 ---- */

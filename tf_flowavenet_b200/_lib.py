@@ -39,6 +39,8 @@ SIGNATURES = {
     "fwn_reverse_host": (_i, [_p, _fp, _fp, _fp, _i, _i, _fp]),
     "fwn_reverse_chunk": (_i, [_p, _fp, _fp, _i, _i, _i, _i, _fp, _p, _l, _p]),
     "fwn_last_launches": (_l, [_p]),
+    "fwn_profile_enable": (_i, [_p, _i]),
+    "fwn_profile_read": (_i, [_p, C.POINTER(C.c_double * 8), C.POINTER(_l * 8), C.POINTER(C.c_double * 8)]),
     "fwn_receptive_halo": (_i, [_p]),
     "fwn_squeeze": (_i, [_fp, _fp, _i, _i, _i, _p]),
     "fwn_unsqueeze": (_i, [_fp, _fp, _i, _i, _i, _p]),

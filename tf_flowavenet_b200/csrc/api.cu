@@ -145,6 +145,17 @@ int fwn_reverse(fwn_handle h, const float* z, const float* c, const int32_t* g, 
 
 int64_t fwn_last_launches(fwn_handle h) { return h ? h->m->launches : -1; }
 
+int fwn_profile_enable(fwn_handle h, int on) {
+  FWN_CHECK(h, "null handle");
+  h->m->prof_on = on != 0;
+  h->m->prof_used = 0;
+  return 0;
+}
+int fwn_profile_read(fwn_handle h, double ms[8], int64_t launches[8], double work[8]) {
+  FWN_CHECK(h && ms && launches && work, "null argument");
+  return prof_read(h->m, ms, launches, work);
+}
+
 // ---- host-buffer convenience: H2D, pass, D2H (what synthesize.py:44-46's sess.run does end to end)
 static int host_buffers(Model* m, int B, int T, float** d_x, float** d_c, float** d_out, float** d_scal) {
   Workspace w;

@@ -136,6 +136,7 @@ int model_create(const fwn_config* cfg, Model** out) {
 
 void model_destroy(Model* m) {
   if (!m) return;
+  for (auto e : m->prof_ev) cudaEventDestroy(e);
   cudaFree(m->raw);
   cudaFree(m->pack);
   cudaFree(m->host_ws);
@@ -452,6 +453,41 @@ int model_prepack(Model* m, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------- optional CUDA-event profiling
+void prof_begin(Model* m, int kind, double work, cudaStream_t st) {
+  if (!m->prof_on) return;
+  if (m->prof_used * 2 + 2 > m->prof_ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      m->prof_ev.push_back(e);
+    }
+    m->prof_kind.push_back(0);
+    m->prof_work.push_back(0);
+  }
+  m->prof_kind[m->prof_used] = kind;
+  m->prof_work[m->prof_used] = work;
+  cudaEventRecord(m->prof_ev[m->prof_used * 2], st);
+}
+void prof_end(Model* m, cudaStream_t st) {
+  if (!m->prof_on) return;
+  cudaEventRecord(m->prof_ev[m->prof_used * 2 + 1], st);
+  m->prof_used++;
+}
+int prof_read(Model* m, double* ms, int64_t* launches, double* work) {
+  for (int k = 0; k < PROF_KINDS; ++k) ms[k] = 0, launches[k] = 0, work[k] = 0;
+  if (m->prof_used) FWN_CUDA(cudaEventSynchronize(m->prof_ev[m->prof_used * 2 - 1]));
+  for (size_t i = 0; i < m->prof_used; ++i) {
+    float t = 0;
+    FWN_CUDA(cudaEventElapsedTime(&t, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+    ms[m->prof_kind[i]] += t;
+    launches[m->prof_kind[i]] += 1;
+    work[m->prof_kind[i]] += m->prof_work[i];
+  }
+  m->prof_used = 0;
+  return 0;
+}
+
 // ---------------------------------------------------------------- workspace plan
 static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -571,6 +607,10 @@ static int run_upsample(const Model* m, const Workspace& w, const float* c_in, i
   for (int i = 0; i < c.n_upsample; ++i) {
     const int s = c.upsample_scales[i];
     const bool last = i == c.n_upsample - 1;
+    // algorithmic bytes: read the stage input once, write the stage output once
+    const double bytes = (double)B * Tm * c.num_mels * 4.0 + (double)B * Tm * s * c.num_mels * (last && bf16 ? 2.0 : 4.0);
+    prof_begin(const_cast<Model*>(m), PROF_UPSAMPLE, bytes, st);
+    const_cast<Model*>(m)->launches++;
     if (last) {
       if (upsample_stage(in, m->up_w[i], m->up_b[i], w.cA, w.cB, B, Tm, c.num_mels, s, true, bf16, st)) return 1;
     } else {
@@ -578,6 +618,7 @@ static int run_upsample(const Model* m, const Workspace& w, const float* c_in, i
       if (upsample_stage(in, m->up_w[i], m->up_b[i], out, nullptr, B, Tm, c.num_mels, s, false, false, st)) return 1;
       in = out;
     }
+    prof_end(const_cast<Model*>(m), st);
     Tm *= s;
   }
   return 0;
@@ -596,7 +637,11 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   fa.an_s = reverse ? nullptr : fp.an_s;
   fa.W = fp.front_w; fa.bias = fp.front_b; fa.H = w.h0; fa.B = B; fa.Ti = Ti; fa.F = F;
   for (int k = 0; k < 3; ++k) fa.shift[k] = shift_of(k, 1);
+  const double rows = (double)B * Ti;
+  prof_begin(m, PROF_FRONT, 2.0 * rows * 3 * fp.nq * F, st);
+  m->launches++;
   if (front_conv(fa, bf16, st)) return 1;
+  prof_end(m, st);
 
   void* hin = w.h0;
   void* hout = w.h1;
@@ -610,7 +655,9 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     g.nseg = 4;
     g.W = fp.gate_w[n]; g.ldw = fp.gate_ld; g.N = 2 * F;
     g.e.bias = fp.gate_b[n]; g.e.out0 = w.o; g.e.F = F;
+    prof_begin(m, PROF_GATE, 2.0 * rows * (3 * F + fp.Kc) * 2 * F, st);
     if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
+    prof_end(m, st);
 
     const bool last = n == L - 1;
     GemmArgs r = {};
@@ -620,7 +667,9 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     r.W = fp.rs_w[n]; r.ldw = fp.rs_ld[n]; r.N = last ? F : 2 * F;
     r.e.bias = fp.rs_b[n]; r.e.F = F; r.e.has_res = !last; r.e.relu = last;
     r.e.in0 = hin; r.e.out0 = hout; r.e.in1 = n > 0 ? w.s : nullptr; r.e.out1 = w.s;
+    prof_begin(m, PROF_RES_SKIP, 2.0 * rows * F * r.N, st);
     if (run_gemm(m, r, EPI_RES_SKIP, GEMM_RS0 + n, fp, st)) return 1;
+    prof_end(m, st);
     std::swap(hin, hout);
   }
   {
@@ -630,7 +679,9 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     g.nseg = 1;
     g.W = fp.final_w; g.ldw = fp.final_ld; g.N = F;
     g.e.bias = fp.final_b; g.e.out0 = w.u; g.e.ld = F; g.e.relu = 1; g.e.F = F;
+    prof_begin(m, PROF_FINAL, 2.0 * rows * F * F, st);
     if (run_gemm(m, g, EPI_PLAIN, GEMM_FINAL, fp, st)) return 1;
+    prof_end(m, st);
   }
   {
     GemmArgs g = {};
@@ -643,7 +694,9 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     g.e.an_b = fp.an_b; g.e.an_s = reverse ? fp.an_is : fp.an_s;
     g.e.logdet_acc = reverse ? nullptr : w.sums;
     g.e.reverse = reverse;
+    prof_begin(m, PROF_ZERO_AFFINE, 2.0 * rows * F * (c.affine ? fp.Cx : fp.nq), st);
     if (run_gemm(m, g, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
+    prof_end(m, st);
   }
   return 0;
 }

@@ -72,7 +72,18 @@ struct Model {
   void* host_io = nullptr;
   int64_t host_io_bytes = 0;
   int64_t launches = 0;  // kernels launched by the last pass (bench.py's gpu_launches)
+  // optional per-kernel-family CUDA-event timing (fwn_profile_*): bench.py's roofline numbers
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_kind;
+  std::vector<double> prof_work;
+  size_t prof_used = 0;
 };
+
+enum ProfKind { PROF_FRONT = 0, PROF_GATE = 1, PROF_RES_SKIP = 2, PROF_FINAL = 3, PROF_ZERO_AFFINE = 4, PROF_UPSAMPLE = 5, PROF_OTHER = 6, PROF_KINDS = 8 };
+void prof_begin(Model* m, int kind, double work, cudaStream_t st);
+void prof_end(Model* m, cudaStream_t st);
+int prof_read(Model* m, double* ms, int64_t* launches, double* work);
 
 int model_create(const fwn_config* cfg, Model** out);
 void model_destroy(Model* m);

@@ -397,6 +397,17 @@ class FloWaveNet:
     def receptive_halo(self):
         return _lib.lib().fwn_receptive_halo(self._h)
 
+    PROFILE_FAMILIES = ("front_conv", "gate_gemm", "res_skip_gemm", "final_conv", "zero_affine", "upsample")
+
+    def profile(self, on=True):
+        _lib.check(_lib.lib().fwn_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """{family: (ms, launches, algorithmic work)} accumulated since the last read (CUDA events on the pass's stream)."""
+        ms, n, w = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)(), (ctypes.c_double * 8)()
+        _lib.check(_lib.lib().fwn_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)))
+        return {k: (ms[i], n[i], w[i]) for i, k in enumerate(self.PROFILE_FAMILIES)}
+
     def last_launches(self):
         return _lib.lib().fwn_last_launches(self._h)
 
