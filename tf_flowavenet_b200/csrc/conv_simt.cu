@@ -269,59 +269,96 @@ int exp3(const float* s, float* out, int n, cudaStream_t st) {
 // ---------------------------------------------------------------- front conv on the flow variable
 // h0[row, ch] = relu(bias[ch] + sum_tap sum_q a(row + shift_tap, q) * W[tap][q][ch]),
 // a(r, q) = ActNorm(X[r, a_off[q]]) (forward) or X[r, a_off[q]] (reverse); zero outside the utterance.
-// K = 3*Cx/2 is 3..384: 384 MAC per audio sample in every block, <0.3% of the pass -> CUDA cores.
-constexpr int FR = 32;  // rows per CTA
+// K = 3*Cx/2 is 3..384: 384 MAC per audio sample in every block, 0.2% of the pass -> CUDA cores, fp32.
+// CTA = 64 rows x 256 channels; a warp owns 8 rows, a lane 8 consecutive channels (64 accumulators), so every
+// output row is written as one 512-byte (bf16) coalesced store.  X is read as ONE contiguous span per CTA.
+constexpr int FR = 64;          // rows per CTA
+constexpr int FRW = FR / 8;     // rows per warp
 template <typename TOut>
 __global__ void __launch_bounds__(256) front_kernel(const FrontArgs a) {
-  extern __shared__ float xs[];  // [3][nq][FR]  (one aligned copy per tap so reads are 128-bit)
-  const int nq = a.nq;
+  extern __shared__ __align__(16) float xs[];  // [3][nq][FR]: one copy per tap, already shifted
+  const int nq = a.nq, Cx = a.Cx;
   const int tiles_per_utt = (a.Ti + FR - 1) / FR;
   const int ub = blockIdx.x / tiles_per_utt;
   const int t0 = (blockIdx.x - ub * tiles_per_utt) * FR;
-  for (int i = threadIdx.x; i < 3 * nq * FR; i += blockDim.x) {
-    const int r = i % FR;
-    const int q = (i / FR) % nq;
-    const int tap = i / (FR * nq);
-    const int t = t0 + r + a.shift[tap];
-    float v = 0.f;
-    if (t >= 0 && t < a.Ti) {
-      const int o = __ldg(a.a_off + q);
-      v = __ldg(a.X + ((int64_t)ub * a.Ti + t) * a.Cx + o);
-      if (a.an_b) v = (v + __ldg(a.an_b + o)) * __ldg(a.an_s + o);
+  int smin = a.shift[0], smax = a.shift[0];
+#pragma unroll
+  for (int k = 1; k < 3; ++k) { smin = min(smin, a.shift[k]); smax = max(smax, a.shift[k]); }
+  for (int i = threadIdx.x; i < 3 * nq * FR; i += blockDim.x) xs[i] = 0.f;
+  __syncthreads();
+  // contiguous span of X covering rows t0+smin .. t0+FR-1+smax of this utterance
+  const int r_lo = max(t0 + smin, 0), r_hi = min(t0 + FR - 1 + smax, a.Ti - 1);
+  const float* xbase = a.X + (int64_t)ub * a.Ti * Cx;
+  for (int64_t i = (int64_t)r_lo * Cx + threadIdx.x; i < (int64_t)(r_hi + 1) * Cx; i += blockDim.x) {
+    const int t = (int)(i / Cx), o = (int)(i - (int64_t)t * Cx);
+    const int q = __ldg(a.off2log + o);  // logical channel; the pass-through half is q < nq
+    if (q >= nq) continue;
+    float v = __ldg(xbase + i);
+    if (a.an_b) v = (v + __ldg(a.an_b + o)) * __ldg(a.an_s + o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int r = t - a.shift[k] - t0;  // output row that reads input row t through tap k
+      if (r >= 0 && r < FR) xs[(k * nq + q) * FR + r] = v;
     }
-    xs[i] = v;
   }
   __syncthreads();
-  for (int ch = threadIdx.x; ch < a.F; ch += blockDim.x) {
-    float acc[FR];
-    const float b = __ldg(a.bias + ch);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ch0 = lane * 8; ch0 < a.F; ch0 += 256) {
+    float acc[FRW][8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + 4));
 #pragma unroll
-    for (int r = 0; r < FR; ++r) acc[r] = b;
-    for (int kq = 0; kq < 3 * nq; ++kq) {
-      const float w = __ldg(a.W + (int64_t)kq * a.F + ch);
-      const float4* xp = reinterpret_cast<const float4*>(xs + kq * FR);
-#pragma unroll
-      for (int r4 = 0; r4 < FR / 4; ++r4) {
-        const float4 x4 = xp[r4];
-        acc[r4 * 4 + 0] = fmaf(x4.x, w, acc[r4 * 4 + 0]);
-        acc[r4 * 4 + 1] = fmaf(x4.y, w, acc[r4 * 4 + 1]);
-        acc[r4 * 4 + 2] = fmaf(x4.z, w, acc[r4 * 4 + 2]);
-        acc[r4 * 4 + 3] = fmaf(x4.w, w, acc[r4 * 4 + 3]);
+      for (int r = 0; r < FRW; ++r) {
+        acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
+        acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
       }
     }
-    TOut* H = reinterpret_cast<TOut*>(a.H);
+    for (int kq = 0; kq < 3 * nq; ++kq) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)kq * a.F + ch0));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)kq * a.F + ch0 + 4));
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + kq * FR + warp * FRW);
+      const float4 x1 = *reinterpret_cast<const float4*>(xs + kq * FR + warp * FRW + 4);
+      const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-    for (int r = 0; r < FR; ++r) {
-      const int t = t0 + r;
-      if (t < a.Ti) H[((int64_t)ub * a.Ti + t) * a.F + ch] = from_f<TOut>(fmaxf(acc[r], 0.f));
+      for (int r = 0; r < FRW; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(x[r], w[j], acc[r][j]);
+    }
+#pragma unroll
+    for (int r = 0; r < FRW; ++r) {
+      const int t = t0 + warp * FRW + r;
+      if (t >= a.Ti) continue;
+      const int64_t off = ((int64_t)ub * a.Ti + t) * a.F + ch0;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[r][j], 0.f);
+      if (sizeof(TOut) == 2) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+        uint4 u = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                             *reinterpret_cast<uint32_t*>(&p3));
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.H) + off) = u;
+      } else {
+        float4* hp = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.H) + off);
+        hp[0] = make_float4(v[0], v[1], v[2], v[3]);
+        hp[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
   }
 }
 int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st) {
   if (a.B <= 0 || a.Ti <= 0) return 0;
+  FWN_CHECK(a.F % 8 == 0, "front_conv: filter size must be a multiple of 8");
   const int tiles_per_utt = (a.Ti + FR - 1) / FR;
   const size_t smem = (size_t)3 * a.nq * FR * sizeof(float);
-  FWN_CHECK(smem <= 48 * 1024, "front_conv: Cx/2=%d too large for the shared-memory tile", a.nq);
+  FWN_CHECK(smem <= 200 * 1024, "front_conv: Cx/2=%d too large for the shared-memory tile", a.nq);
+  static bool configured = false;
+  if (!configured) {
+    FWN_CUDA(cudaFuncSetAttribute(front_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FWN_CUDA(cudaFuncSetAttribute(front_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
   if (bf16_out) front_kernel<__nv_bfloat16><<<a.B * tiles_per_utt, 256, smem, st>>>(a);
   else front_kernel<float><<<a.B * tiles_per_utt, 256, smem, st>>>(a);
   FWN_LAUNCH_CHECK();

@@ -342,6 +342,56 @@ __global__ void upsample_kernel(const float* __restrict__ in, const float* __res
     }
   }
 }
+// Vectorised variant for the fused path's split bf16/fp32 planes: one thread = 8 consecutive mel bins of one
+// output time step (requires mels/2 % 8 == 0): 2 x 10 input values, 48 FMA, one 16-byte (bf16) store.
+template <typename TOut>
+__global__ void upsample_split8_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias_p,
+                                       TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < 2 * s * 3; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int To = Tm * s, half = mels / 2, g_per_t = mels / 8;
+  const int64_t n = (int64_t)B * To * g_per_t;
+  const float bias = __ldg(bias_p);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int gi = (int)(idx % g_per_t);
+    const int64_t bt = idx / g_per_t;
+    const int i = (int)(bt % To), b = (int)(bt / To);
+    const int m0 = gi * 8;
+    const int q = i + s / 2, r = q % s, j0 = q / s;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int jj = j0 - a, kh = r + a * s;
+      if (jj < 0 || jj >= Tm) continue;
+      const float* row = in + ((int64_t)b * Tm + jj) * mels;
+      float xv[10];
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        const int mm = m0 - 1 + u;
+        xv[u] = (mm >= 0 && mm < mels) ? __ldg(row + mm) : 0.f;
+      }
+      const float w0 = sw[kh * 3 + 0], w1 = sw[kh * 3 + 1], w2 = sw[kh * 3 + 2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)  // out[m] += in[m+1] w[.,0] + in[m] w[.,1] + in[m-1] w[.,2]
+        acc[j] = fmaf(xv[j + 2], w0, fmaf(xv[j + 1], w1, fmaf(xv[j], w2, acc[j])));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.4f * acc[j]);
+    TOut* dst = (m0 < half) ? out0 + bt * half + m0 : out1 + bt * half + (m0 - half);
+    if (sizeof(TOut) == 2) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                  *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    } else {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
 // weight norm of the [2s,3,1,1] kernel over axes [0,2] => per kw column (convolutional.py:186)
 __global__ void upsample_wn_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int s) {
   int kw = threadIdx.x;
@@ -363,6 +413,11 @@ int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* o
   if (n == 0) return 0;
   int grid = ew_grid(n, 256);
   size_t smem = 2 * (size_t)s * 3 * sizeof(float);
+  if (split && (mels / 2) % 8 == 0) {
+    upsample_split8_kernel<TOut><<<ew_grid(n / 8, 256), 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    FWN_LAUNCH_CHECK();
+    return 0;
+  }
   if (split) upsample_kernel<TOut, true><<<grid, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
   else upsample_kernel<TOut, false><<<grid, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
   FWN_LAUNCH_CHECK();

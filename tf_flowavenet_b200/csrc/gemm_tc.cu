@@ -13,7 +13,8 @@
 // * Epilogue warps read TMEM with tcgen05.ld (each thread owns one output row) and apply the fused flow op:
 //   tanh*sigmoid gate, residual + skip accumulation, bias+ReLU, or ActNorm + affine coupling + log-det in place on x.
 // Persistent grid (<= one CTA per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-5 epilogue.
+// warps 2-9 epilogue (two warps per TMEM lane group, each owning half of the tile's columns; the residual / skip
+// inputs of a tile are prefetched into registers before the accumulator is waited for, so their HBM latency is hidden).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,12 +25,16 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane group)
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_SEG = 4;
 
 struct alignas(64) TcArgs {
   CUtensorMap mapA[MAX_SEG];
   CUtensorMap mapB;
+  CUtensorMap mapIn[2];      // RES_SKIP: [0] residual input h_in, [1] running skip sum (same (64,128,1) swizzled boxes)
+  CUtensorMap mapOut[2];     // GATE: [0]=o; RES_SKIP: [0]=h_out, [1]=skip; PLAIN: [0]=y
+  int has_in[2];
   int shift[MAX_SEG];
   int nchunk[MAX_SEG];       // 64-wide K chunks in the segment
   int last_ksteps[MAX_SEG];  // valid 16-wide MMA steps in the segment's last chunk (1..4)
@@ -81,6 +86,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, 
           smem_u32(smem)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(smem)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -154,28 +164,52 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
   hi = __high2float(v);
 }
 
-template <int BN>
+// Per-(epilogue, tile-width) configuration.  STAGED epilogues move their tiles through 128B-swizzled shared memory:
+// outputs leave with TMA bulk stores and the residual / running-skip inputs arrive with TMA bulk loads, so no
+// warp ever issues row-strided (32 lines per instruction) global accesses.
+// WS (weight-stationary): the CTA owns ONE column tile for its whole life; that tile's weights (K <= 256, i.e. <= 4
+// chunks) are loaded once into shared memory and only activations stream through the (A-only, deeper) pipeline.
+// Used by the K=256 1x1 GEMMs (res|skip, final) whose per-tile weight traffic otherwise dwarfs their MMA time.
+template <int EPI, int BN, bool WS>
 struct Cfg {
+  static constexpr bool STAGED = (EPI == EPI_GATE) || (EPI == EPI_RES_SKIP) || (EPI == EPI_PLAIN && BN >= 128);
+  static constexpr bool IN_PLACE = (EPI == EPI_RES_SKIP);                 // staging tile is TMA-loaded, updated in place, TMA-stored
+  static constexpr int OUT_COLS = (EPI == EPI_GATE) ? BN / 2 : BN;        // bf16 output columns per tile
+  static constexpr int SUBTILES = STAGED ? OUT_COLS / 64 : 0;             // [128 rows x 64 cols] 16 KB boxes
+  static constexpr int STG_BYTES = SUBTILES * BM * 128;
+  // staging ring depth: in-place tiles need 3 so the input load of tile i+2 is issued while tile i+1 is processed;
+  // plain staged stores use 2 when shared memory allows (WS), so a tile never waits for the store issued just before it
+  static constexpr int NSTG = STAGED ? (IN_PLACE ? 3 : (WS ? 2 : 1)) : 0;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int WS_CHUNKS = 4;
+  static constexpr int W_BYTES = WS ? WS_CHUNKS * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int BUDGET = 225 * 1024 - NSTG * STG_BYTES - W_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int BIAS_FLOATS = 512;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + BIAS_FLOATS * 4 + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + 256;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
+// byte offset of the 16-byte chunk holding columns [c, c+8) of row r inside a staged tile (TMA SWIZZLE_128B layout)
+__device__ __forceinline__ uint32_t stg_off(int r, int c) {
+  return (uint32_t)((c >> 6) * (BM * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
+}
+
 // ---------------------------------------------------------------- epilogue on 16 accumulator columns of one row
-template <int EPI, int BN>
-__device__ __forceinline__ void epilogue16(const TcArgs& a, const float* sbias, int64_t row, bool row_ok, int n_tile, int c0, const uint32_t* v,
-                                           double& ls_sum) {
+// `stg` = this tile's staging buffer (STAGED kinds); for RES_SKIP it already holds the residual input / running skip sum.
+template <int EPI, int BN, bool WS>
+__device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool row_ok, int r, int n_tile, int c0, const uint32_t* v,
+                                           uint8_t* stg, bool have_in, double& ls_sum) {
+  using C = Cfg<EPI, BN, WS>;
   const EpiArgs& e = a.e;
   const int col = n_tile * BN + c0;  // global column of v[0]
   float acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + sbias[col + j];
-  if (!row_ok) return;
+  for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + ((col + j < a.N) ? __ldg(e.bias + col + j) : 0.f);
   if (EPI == EPI_GATE) {
-    // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124)
+    // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124); 16 columns -> 8 channels = one 16-byte chunk
     uint32_t p[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -183,49 +217,37 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, const float* sbias, 
       float o1 = tanh_fast(acc[4 * j + 2]) * sigmoid_fast(acc[4 * j + 3]);
       p[j] = pack_bf16(o0, o1);
     }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.F + col / 2;
-    *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+    *reinterpret_cast<uint4*>(stg + stg_off(r, c0 / 2)) = make_uint4(p[0], p[1], p[2], p[3]);
   } else if (EPI == EPI_RES_SKIP) {
-    const int F = e.F;
-    if (e.has_res && col < F) {  // h_out = (h_in + res) * sqrt(.5)   (modules.py:128)
-      const uint4* hp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + row * F + col);
-      uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+    uint4* q0 = reinterpret_cast<uint4*>(stg + stg_off(r, c0));
+    uint4* q1 = reinterpret_cast<uint4*>(stg + stg_off(r, c0 + 8));
+    const bool is_res = e.has_res && col < e.F;
+    if (have_in) {
+      const uint4 h0 = *q0, h1 = *q1;
       const uint32_t hu[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-      uint32_t p[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float lo, hi;
         unpack_bf16(hu[j], lo, hi);
-        p[j] = pack_bf16((lo + acc[2 * j]) * 0.70710678118654752440f, (hi + acc[2 * j + 1]) * 0.70710678118654752440f);
+        acc[2 * j] += lo;
+        acc[2 * j + 1] += hi;
       }
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out0) + row * F + col);
-      op[0] = make_uint4(p[0], p[1], p[2], p[3]);
-      op[1] = make_uint4(p[4], p[5], p[6], p[7]);
-    } else {  // skip (+ running sum, + ReLU on the last layer)   (modules.py:127,176-177)
-      const int c = e.has_res ? col - F : col;
-      if (e.in1) {
-        const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + row * F + c);
-        uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-        const uint32_t su[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float lo, hi;
-          unpack_bf16(su[j], lo, hi);
-          acc[2 * j] += lo;
-          acc[2 * j + 1] += hi;
-        }
-      }
-      uint32_t p[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float lo = acc[2 * j], hi = acc[2 * j + 1];
-        if (e.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-        p[j] = pack_bf16(lo, hi);
-      }
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out1) + row * F + c);
-      op[0] = make_uint4(p[0], p[1], p[2], p[3]);
-      op[1] = make_uint4(p[4], p[5], p[6], p[7]);
     }
+    uint32_t p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float lo = acc[2 * j], hi = acc[2 * j + 1];
+      if (is_res) {  // h_out = (h_in + res) * sqrt(.5)   (modules.py:128)
+        lo *= 0.70710678118654752440f;
+        hi *= 0.70710678118654752440f;
+      } else if (e.relu) {  // last layer: relu(sum of skips) feeds Conv_final (modules.py:176-177)
+        lo = fmaxf(lo, 0.f);
+        hi = fmaxf(hi, 0.f);
+      }
+      p[j] = pack_bf16(lo, hi);
+    }
+    *q0 = make_uint4(p[0], p[1], p[2], p[3]);
+    *q1 = make_uint4(p[4], p[5], p[6], p[7]);
   } else if (EPI == EPI_PLAIN) {
     uint32_t p[8];
 #pragma unroll
@@ -234,18 +256,24 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, const float* sbias, 
       if (e.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
       p[j] = pack_bf16(lo, hi);
     }
-    if (col + 15 < a.N) {
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col);
-      op[0] = make_uint4(p[0], p[1], p[2], p[3]);
-      op[1] = make_uint4(p[4], p[5], p[6], p[7]);
-    } else {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col;
+    if (C::STAGED) {
+      *reinterpret_cast<uint4*>(stg + stg_off(r, c0)) = make_uint4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<uint4*>(stg + stg_off(r, c0 + 8)) = make_uint4(p[4], p[5], p[6], p[7]);
+    } else if (row_ok) {
+      if (col + 15 < a.N) {
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col);
+        op[0] = make_uint4(p[0], p[1], p[2], p[3]);
+        op[1] = make_uint4(p[4], p[5], p[6], p[7]);
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col + j < a.N) o[j] = __float2bfloat16_rn(e.relu ? fmaxf(acc[j], 0.f) : acc[j]);
+        for (int j = 0; j < 16; ++j)
+          if (col + j < a.N) o[j] = __float2bfloat16_rn(e.relu ? fmaxf(acc[j], 0.f) : acc[j]);
+      }
     }
   } else if (EPI == EPI_AFFINE) {
     // (2q, 2q+1) = (log_s, t) of transformed element q; ActNorm + coupling in place on the fp32 flow variable
+    if (!row_ok) return;
     float* xr = e.X + row * e.Cx;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -271,21 +299,41 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, const float* sbias, 
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int EPI, int BN>
+template <int EPI, int BN, bool WS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcArgs a) {
-  using C = Cfg<BN>;
+  using C = Cfg<EPI, BN, WS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* sbias = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + C::BIAS_FLOATS);
+  uint8_t* w_base = smem + (size_t)C::STAGES * C::STAGE_BYTES;   // WS: resident weight chunks
+  uint8_t* stg_base = w_base + C::W_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (size_t)C::NSTG * C::STG_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* in_full = tmem_empty + 2;   // staged inputs landed (RES_SKIP)
+  uint64_t* in_empty = in_full + 3;     // staging buffer may be overwritten by the next input load
+  uint64_t* w_full = in_empty + 3;      // WS: resident weights landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.B * a.tiles_per_utt * a.n_tiles;
+  const int num_m_tiles = a.B * a.tiles_per_utt;
+  // tile schedule.  streaming: tile = blockIdx.x + it*gridDim.x over (m, n) with n fastest.
+  // weight-stationary: n fixed per CTA, m strides by gridDim.x / n_tiles (host guarantees gridDim.x % n_tiles == 0).
+  const int ws_groups = WS ? (int)gridDim.x / a.n_tiles : 1;
+  const int ws_n = WS ? (int)blockIdx.x % a.n_tiles : 0;
+  const int ws_m0 = WS ? (int)blockIdx.x / a.n_tiles : 0;
+  auto tile_of = [&](int it, int& m_tile, int& n_tile) -> bool {
+    if (WS) {
+      m_tile = ws_m0 + it * ws_groups;
+      n_tile = ws_n;
+      return m_tile < num_m_tiles;
+    }
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    m_tile = tile / a.n_tiles;
+    n_tile = tile - m_tile * a.n_tiles;
+    return tile < num_m_tiles * a.n_tiles;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.nseg; ++s) prefetch_tmap(&a.mapA[s]);
@@ -296,36 +344,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 128);
+      mbar_init(tmem_empty + i, EPI_THREADS);
     }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(in_full + i, 1);
+      mbar_init(in_empty + i, 1);
+    }
+    mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
-  for (int i = threadIdx.x; i < C::BIAS_FLOATS; i += NUM_THREADS) {
-    const int npad = a.n_tiles * BN;
-    sbias[i] = (i < npad && i < a.N) ? __ldg(a.e.bias + i) : 0.f;
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+
+  // which input map (if any) feeds the epilogue of column tile n_tile (RES_SKIP only)
+  auto input_map_of = [&](int n_tile) -> int {
+    if (EPI != EPI_RES_SKIP) return -1;
+    const int which = (a.e.has_res && n_tile * BN < a.e.F) ? 0 : 1;
+    return a.has_in[which] ? which : -1;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+      int m_tile, n_tile;
+      if (WS) {  // resident weights: every K chunk of this CTA's column tile, once
+        int nch = 0;
+        for (int s = 0; s < a.nseg; ++s) nch += a.nchunk[s];
+        mbar_expect_tx(w_full, (uint32_t)nch * C::B_BYTES);
+        int c = 0;
+        for (int s = 0; s < a.nseg; ++s)
+          for (int ch = 0; ch < a.nchunk[s]; ++ch, ++c)
+            tma_load_2d(w_base + (size_t)c * C::B_BYTES, &a.mapB, w_full, a.wk0[s] + ch * BK, ws_n * BN);
+      }
+      for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
         const int ub = m_tile / a.tiles_per_utt;
         const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
+        if (C::IN_PLACE) {
+          // epilogue input tile -> staging buffer it % NSTG; the buffer is free once the TMA store that last used it has read it
+          const int b = it % C::NSTG;
+          mbar_wait(in_empty + b, ((it / C::NSTG) & 1) ^ 1);
+          const int im = input_map_of(n_tile);
+          if (im >= 0) {
+            const int cin0 = (n_tile * BN) % a.e.F;  // column of this tile inside the [rows, F] input tensor
+            mbar_expect_tx(in_full + b, C::STG_BYTES);
+#pragma unroll
+            for (int j = 0; j < C::SUBTILES; ++j)
+              tma_load_3d(stg_base + (size_t)b * C::STG_BYTES + (size_t)j * BM * 128, &a.mapIn[im], in_full + b, cin0 + j * 64, t0, ub);
+          } else {
+            mbar_arrive(in_full + b);
+          }
+        }
         for (int s = 0; s < a.nseg; ++s) {
           for (int ch = 0; ch < a.nchunk[s]; ++ch) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * C::STAGE_BYTES;
             mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
             tma_load_3d(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
-            tma_load_2d(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN);
+            if (!WS) tma_load_2d(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -336,18 +416,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     constexpr uint32_t idesc = make_idesc<BN>();
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int m_tile, n_tile;
+    if (WS) {
+      mbar_wait(w_full, 0);
+      tcgen05_fence_after();
+    }
+    for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
       mbar_wait(tmem_empty + as, aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
       uint32_t accumulate = 0;
+      int c = 0;
       for (int s = 0; s < a.nseg; ++s) {
-        for (int ch = 0; ch < a.nchunk[s]; ++ch) {
+        for (int ch = 0; ch < a.nchunk[s]; ++ch, ++c) {
           mbar_wait(full_bar + stage, phase);
           tcgen05_fence_after();
           if (lane == 0) {
             const uint32_t sa = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
-            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+            const uint32_t sb = WS ? smem_u32(w_base + (size_t)c * C::B_BYTES) : sa + A_BYTES;
+            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
             const int ksteps = (ch == a.nchunk[s] - 1) ? a.last_ksteps[s] : BK / UMMA_K;
             for (int k = 0; k < ksteps; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte address units
@@ -366,34 +453,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int lg = warp & 3;              // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp owns
     const int r = lg * 32 + lane;
+    constexpr int CW = BN >= 32 ? BN / 2 : BN;  // accumulator columns per warp
+    const bool active = (BN >= 32) || half == 0;
+    const int cbeg = half * CW;
+    const bool elected = (threadIdx.x == 64);   // first epilogue thread issues the TMA stores
     int as = 0;
     uint32_t aphase = 0;
     double ls_sum = 0.0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+    int m_tile, n_tile;
+    for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
       const int ub = m_tile / a.tiles_per_utt;
-      const int t = (m_tile - ub * a.tiles_per_utt) * BM + r;
+      const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
+      const int t = t0 + r;
       const bool row_ok = t < a.Ti;
       const int64_t row = (int64_t)ub * a.Ti + t;
+      const int b = C::STAGED ? it % C::NSTG : 0;
+      uint8_t* stg = stg_base + (size_t)b * C::STG_BYTES;
+      bool have_in = false;
+      if (C::STAGED && !C::IN_PLACE) {
+        // the store that last used this staging buffer (NSTG tiles ago) must have finished READING it before we overwrite it
+        if (elected) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NSTG > 0 ? C::NSTG - 1 : 0) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      }
+      if (C::IN_PLACE) {
+        have_in = input_map_of(n_tile) >= 0;
+        mbar_wait(in_full + b, (it / C::NSTG) & 1);
+      }
       mbar_wait(tmem_full + as, aphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x16(taddr + c0, v);
-        if (BN > 16) tmem_ld_x16(taddr + c0 + 16, v + 16);
-        tmem_ld_wait();
-        epilogue16<EPI, BN>(a, sbias, row, row_ok, n_tile, c0, v, ls_sum);
-        if (BN > 16) epilogue16<EPI, BN>(a, sbias, row, row_ok, n_tile, c0 + 16, v + 16, ls_sum);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cbeg);
+      if (active) {
+#pragma unroll
+        for (int cc = 0; cc < CW; cc += 32) {
+          uint32_t v[32];
+          tmem_ld_x16(taddr + cc, v);
+          if (CW > 16) tmem_ld_x16(taddr + cc + 16, v + 16);
+          tmem_ld_wait();
+          epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cbeg + cc, v, stg, have_in, ls_sum);
+          if (CW > 16) epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cbeg + cc + 16, v + 16, stg, have_in, ls_sum);
+        }
       }
       tcgen05_fence_before();
-      mbar_arrive(tmem_empty + as);
+      mbar_arrive(tmem_empty + as);   // accumulator drained: the MMA warp may start tile it+2 in this TMEM stage
       if (++as == 2) { as = 0; aphase ^= 1; }
+      if (C::STAGED) {
+        // generic-proxy writes -> visible to the async proxy, then one thread issues the bulk stores (rows >= Ti are clipped by TMA)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (elected) {
+          int om = 0, ocol = n_tile * C::OUT_COLS;
+          if (EPI == EPI_RES_SKIP) {
+            om = (a.e.has_res && n_tile * BN < a.e.F) ? 0 : 1;
+            ocol = (n_tile * BN) % a.e.F;
+          }
+#pragma unroll
+          for (int j = 0; j < C::SUBTILES; ++j)
+            tma_store_3d(&a.mapOut[om], stg + (size_t)j * BM * 128, ocol + j * 64, t0, ub);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (C::IN_PLACE) {
+            // all but the newest store have read their staging buffer -> the buffer of tile it-1 may be refilled (for tile it+2)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (it >= 1) mbar_arrive(in_empty + ((it - 1) % C::NSTG));
+          }
+        }
+      }
     }
+    if (C::STAGED && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (EPI == EPI_AFFINE) {
       if (!a.e.reverse && a.e.logdet_acc) {
         ls_sum = warp_sum(ls_sum);
@@ -451,48 +580,61 @@ int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
   return 0;
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool WS>
 static int launch(const TcArgs& a, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<EPI, BN, WS>;
   static bool configured = false;
   if (!configured) {
-    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
-  const int total = a.B * a.tiles_per_utt * a.n_tiles;
-  const int grid = std::min(total, num_sms());
-  tc_gemm_kernel<EPI, BN><<<grid, NUM_THREADS, C::SMEM, st>>>(a);
+  const int num_m = a.B * a.tiles_per_utt;
+  int grid;
+  if (WS) {
+    int nch = 0;
+    for (int s = 0; s < a.nseg; ++s) nch += a.nchunk[s];
+    FWN_CHECK(nch <= C::WS_CHUNKS, "weight-stationary GEMM needs K <= 256");
+    const int groups = std::max(1, std::min(num_m, num_sms() / a.n_tiles));
+    grid = groups * a.n_tiles;
+  } else {
+    grid = std::min(num_m * a.n_tiles, num_sms());
+  }
+  tc_gemm_kernel<EPI, BN, WS><<<grid, NUM_THREADS, C::SMEM, st>>>(a);
   FWN_LAUNCH_CHECK();
   return 0;
 }
 
-int block_n_for(EpiKind kind, int N) {
-  if (kind != EPI_AFFINE && kind != EPI_PLAIN) return 256;
+// tile width per GEMM family: the two 1x1 K=256 GEMMs of the model path run weight-stationary at BN=128
+int block_n_for(EpiKind kind, int N, bool model_path) {
+  if (kind == EPI_GATE) return 256;
+  if (kind == EPI_RES_SKIP) return 128;
+  if (kind == EPI_PLAIN && model_path) return 128;
   int bn = 16;
   while (bn < N && bn < 256) bn *= 2;
   return bn;
 }
 
-int tc_launch(TcArgs& a, EpiKind kind, int bn, cudaStream_t st) {
-  FWN_CHECK(a.n_tiles * bn <= Cfg<256>::BIAS_FLOATS, "tc_gemm: N=%d too wide", a.N);
+int tc_launch(TcArgs& a, EpiKind kind, int bn, bool ws, cudaStream_t st) {
+  FWN_CHECK(a.n_tiles * bn <= 512, "tc_gemm: N=%d too wide", a.N);
   switch (kind) {
-    case EPI_GATE: FWN_CHECK(bn == 256, "gate needs BN=256"); return launch<EPI_GATE, 256>(a, st);
-    case EPI_RES_SKIP: FWN_CHECK(bn == 256, "res/skip needs BN=256"); return launch<EPI_RES_SKIP, 256>(a, st);
+    case EPI_GATE: FWN_CHECK(bn == 256, "gate needs BN=256"); return launch<EPI_GATE, 256, false>(a, st);
+    case EPI_RES_SKIP: FWN_CHECK(bn == 128 && ws, "res/skip runs weight-stationary at BN=128"); return launch<EPI_RES_SKIP, 128, true>(a, st);
     case EPI_PLAIN:
+      if (ws) { FWN_CHECK(bn == 128, "weight-stationary plain GEMM needs BN=128"); return launch<EPI_PLAIN, 128, true>(a, st); }
       switch (bn) {
-        case 16: return launch<EPI_PLAIN, 16>(a, st);
-        case 32: return launch<EPI_PLAIN, 32>(a, st);
-        case 64: return launch<EPI_PLAIN, 64>(a, st);
-        case 128: return launch<EPI_PLAIN, 128>(a, st);
-        default: return launch<EPI_PLAIN, 256>(a, st);
+        case 16: return launch<EPI_PLAIN, 16, false>(a, st);
+        case 32: return launch<EPI_PLAIN, 32, false>(a, st);
+        case 64: return launch<EPI_PLAIN, 64, false>(a, st);
+        case 128: return launch<EPI_PLAIN, 128, false>(a, st);
+        default: return launch<EPI_PLAIN, 256, false>(a, st);
       }
     case EPI_AFFINE:
       switch (bn) {
-        case 16: return launch<EPI_AFFINE, 16>(a, st);
-        case 32: return launch<EPI_AFFINE, 32>(a, st);
-        case 64: return launch<EPI_AFFINE, 64>(a, st);
-        case 128: return launch<EPI_AFFINE, 128>(a, st);
-        default: return launch<EPI_AFFINE, 256>(a, st);
+        case 16: return launch<EPI_AFFINE, 16, false>(a, st);
+        case 32: return launch<EPI_AFFINE, 32, false>(a, st);
+        case 64: return launch<EPI_AFFINE, 64, false>(a, st);
+        case 128: return launch<EPI_AFFINE, 128, false>(a, st);
+        default: return launch<EPI_AFFINE, 256, false>(a, st);
       }
   }
   return 1;
@@ -541,7 +683,7 @@ int tc_prepare(Model* m, const Workspace& w, int B, int T, cudaStream_t st) {
   for (size_t f = 0; f < m->flows.size(); ++f) {
     const FlowPack& fp = m->flows[f];
     auto mk = [&](int id, const void* wptr, int N, int Kpad, EpiKind kind) {
-      const int bn = tc::block_n_for(kind, N);
+      const int bn = tc::block_n_for(kind, N, true);
       const int Npad = (N + 15) / 16 * 16;
       p->wbn[f * GEMM_IDS + id] = bn;
       return tc::make_w_map(&p->wmap[f * GEMM_IDS + id], wptr, Npad, Kpad, std::min(bn, Npad));
@@ -578,6 +720,24 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
     a.wk0[s] = g.seg[s].koff;
   }
   a.mapB = p->wmap[f * GEMM_IDS + gemm_id];
+  auto act_map = [&](const void* ptr, CUtensorMap* dst) -> bool {
+    const int ai = ptr ? act_index(p->w, ptr) : -1;
+    if (ai < 0) return false;
+    *dst = p->act[(size_t)block * 7 + ai];
+    return true;
+  };
+  if (kind == EPI_GATE) {
+    FWN_CHECK(act_map(g.e.out0, &a.mapOut[0]), "tc_run: gate output is not a planned buffer");
+  } else if (kind == EPI_RES_SKIP) {
+    if (g.e.has_res) {
+      FWN_CHECK(act_map(g.e.out0, &a.mapOut[0]) && act_map(g.e.in0, &a.mapIn[0]), "tc_run: residual buffers are not planned buffers");
+      a.has_in[0] = 1;
+    }
+    FWN_CHECK(act_map(g.e.out1, &a.mapOut[1]), "tc_run: skip output is not a planned buffer");
+    a.has_in[1] = act_map(g.e.in1, &a.mapIn[1]) ? 1 : 0;
+  } else if (kind == EPI_PLAIN) {
+    FWN_CHECK(act_map(g.e.out0, &a.mapOut[0]), "tc_run: output is not a planned buffer");
+  }
   const int bn = p->wbn[f * GEMM_IDS + gemm_id];
   a.B = g.B;
   a.Ti = g.Ti;
@@ -585,7 +745,8 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   a.N = g.N;
   a.n_tiles = (g.N + bn - 1) / bn;
   a.e = g.e;
-  return tc::tc_launch(a, kind, bn, st);
+  const bool ws = (kind == EPI_RES_SKIP) || (kind == EPI_PLAIN);
+  return tc::tc_launch(a, kind, bn, ws, st);
 }
 
 // Stand-alone mixed-precision conv (per-op entry fwn_conv1d_bf16): y = [relu](conv(x, w) + bias), bf16 in/out.
@@ -596,7 +757,7 @@ int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, i
   tc::TcArgs a;
   memset(&a, 0, sizeof(a));
   const int Cin16 = (Cin + 15) / 16 * 16, Kpad = (ksize * Cin16 + 63) / 64 * 64, Npad = (Cout + 15) / 16 * 16;
-  const int bn = tc::block_n_for(EPI_PLAIN, Cout);
+  const int bn = tc::block_n_for(EPI_PLAIN, Cout, false);
   const int pad = causal ? dilation * (ksize - 1) : dilation * (ksize - 1) / 2;
   a.nseg = ksize;
   for (int k = 0; k < ksize; ++k) {
@@ -609,7 +770,8 @@ int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, i
   if (tc::make_w_map(&a.mapB, w, Npad, Kpad, std::min(bn, Npad))) return 1;
   a.B = B; a.Ti = T; a.tiles_per_utt = (T + tc::BM - 1) / tc::BM; a.N = Cout; a.n_tiles = (Cout + bn - 1) / bn;
   a.e.bias = bias; a.e.out0 = y; a.e.ld = Cout; a.e.relu = relu; a.e.F = Cout;
-  return tc::tc_launch(a, EPI_PLAIN, bn, st);
+  if (bn >= 128 && tc::make_act_map(&a.mapOut[0], y, B, T, Cout, Cout)) return 1;  // staged TMA-store epilogue
+  return tc::tc_launch(a, EPI_PLAIN, bn, false, st);
 }
 
 void tc_free(Model* m) {

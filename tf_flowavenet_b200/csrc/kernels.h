@@ -74,7 +74,7 @@ int weight_norm_scale(const float* v, const float* g, float* scale, int K, int C
 int exp3(const float* s, float* out, int n, cudaStream_t st);
 // front conv of the coupling WaveNet, reading the flow variable X directly (optional ActNorm on load)
 struct FrontArgs {
-  const float* X; int Cx; int nq; const int* a_off;
+  const float* X; int Cx; int nq; const int* a_off; const int* off2log;
   const float* an_b; const float* an_s;  // null -> identity (reverse direction)
   const float* W;   // [3][nq][F] fp32
   const float* bias; // [F]

@@ -632,7 +632,7 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   auto shift_of = [&](int k, int d) { return c.causal ? (k - 2) * d : (k - 1) * d; };  // modules.py:12-15,27
 
   FrontArgs fa;
-  fa.X = X; fa.Cx = fp.Cx; fa.nq = fp.nq; fa.a_off = fp.a_off;
+  fa.X = X; fa.Cx = fp.Cx; fa.nq = fp.nq; fa.a_off = fp.a_off; fa.off2log = fp.off2log;
   fa.an_b = reverse ? nullptr : fp.an_b;
   fa.an_s = reverse ? nullptr : fp.an_s;
   fa.W = fp.front_w; fa.bias = fp.front_b; fa.H = w.h0; fa.B = B; fa.Ti = Ti; fa.F = F;
