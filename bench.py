@@ -31,6 +31,8 @@ WORKLOADS = {
     "c2": ("hparams", "forward", 8, 63, "float32", "C2: hparams forward log-likelihood, 8 x 16128 samples, fp32"),
     "c4": ("hparams", "reverse", 1, 5168, "bfloat16", "C4: hparams inverse synthesis, 1 utterance x 60 s (T=1323008), mixed precision, single GPU"),
     "c1m": ("hparams", "reverse", 1, 87, "bfloat16", "C1 shape in mixed precision"),
+    "c4s": ("hparams", "reverse", 1, 5168, "bfloat16", "C4: hparams inverse synthesis, ONE 60 s utterance (T=1323008) sharded by time chunk across the GPUs, "
+            "15616-sample receptive-field halos exchanged with NCCL send/recv, mixed precision"),
 }
 MFLOP_PER_SAMPLE = {"hparams": 17.31174, "hparams8000": 15.448592}  # SURVEY 8d algorithmic 2*MAC per audio sample
 
@@ -157,7 +159,18 @@ def main():
 
     net = P.FloWaveNet(P.HParams(**{**hp_ref.values(), "dtype": dtype}), variables=P.VariableStore())
     net.load_variables(synthetic_params(net.variable_shapes(), seed=1234))
-    a_np, c_np = synthetic_inputs(hop, 80, B, n_frames, 1234 + 3 + rank, "z" if direction == "reverse" else "x")
+    sharded = args.workload == "c4s"
+    if sharded:
+        assert n_frames % world == 0, "c4s needs the frame count to divide by the number of GPUs"
+        full_a, full_c = synthetic_inputs(hop, 80, B, n_frames, 1234 + 3, "z")     # same utterance on every rank ...
+        n_frames //= world                                                          # ... of which this rank owns one time chunk
+        a_np = np.ascontiguousarray(full_a[:, rank * n_frames * hop:(rank + 1) * n_frames * hop])
+        c_np = np.ascontiguousarray(full_c[:, rank * n_frames:(rank + 1) * n_frames])
+        T = n_frames * hop
+        config.update(scaling_note="strong scaling: total work fixed (one utterance), chunk per GPU = %d samples + halos" % T,
+                      parallelism="time-chunk sharded x%d, halo exchange = NCCL P2P with rank+-1" % world)
+    else:
+        a_np, c_np = synthetic_inputs(hop, 80, B, n_frames, 1234 + 3 + rank, "z" if direction == "reverse" else "x")
     # ActNorm data-dependent init on a small batch of the same distribution (train.py:221,229)
     xi, ci = synthetic_inputs(hop, 80, min(B, 2), min(n_frames, 64), 99, "x")
     net.initialize_actnorm(torch.from_numpy(xi).cuda(), torch.from_numpy(ci).cuda())
@@ -166,10 +179,16 @@ def main():
     out_pin = torch.empty(B, T, 1, dtype=torch.float32).pin_memory()
 
     def step_dev():
+        if sharded:
+            return net.reverse_sharded(a_dev, c_dev, rank, world)
         return net.reverse(a_dev, c_dev) if direction == "reverse" else net.forward(a_dev, c_dev)
 
     def step_e2e():
-        if direction == "reverse":
+        if sharded:  # host chunk in, halo exchange on device, host chunk out
+            x = net.reverse_sharded(a_pin.cuda(non_blocking=True), c_pin.cuda(non_blocking=True), rank, world)
+            out_pin.copy_(x, non_blocking=True)
+            torch.cuda.synchronize()
+        elif direction == "reverse":
             net.reverse_host(a_pin, c_pin, out_pin)
         else:
             net.forward_host(a_pin, c_pin)
@@ -237,7 +256,7 @@ def main():
     bytes_in = a_pin.numel() * 4 + c_pin.numel() * 4
     bytes_out = out_pin.numel() * 4 if direction == "reverse" else 8
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "bf16" if dtype == "bfloat16" else "f32", "data": "synthetic", "config": config, "roofline": roof, "clocks": clk,
             "e2e": {"value": samples_per_step * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": bytes_in,
                     "d2h_bytes_per_step": bytes_out, "api": "FloWaveNet.reverse_host -> fwn_reverse_host (pinned host buffers)"},

@@ -121,8 +121,9 @@ def test_host_entry_points_and_chunked_synthesis():
     from tf_flowavenet_b200 import _lib
     hp = O.HP(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=(2, 2))
     net = make_model(hp, O.synthetic_params(hp, 3))
+    from tf_flowavenet_b200 import sharding
     halo = net.receptive_halo()
-    assert halo % 4 == 0 and halo >= 2 * 5 * (2 + 4)
+    assert halo % 4 == 0 and halo == sharding.receptive_halo(hp)
     frames = (4 * halo) // 4
     z, c = O.synthetic_inputs(hp, 1, frames, 4, "z")
     T = z.shape[1]
@@ -146,3 +147,6 @@ def test_host_entry_points_and_chunked_synthesis():
         outs.append(xo)
     got = torch.cat(outs, 1)
     assert (got - full).abs().max() < 1e-5
+    # the Python wrapper of the same entry point, as used by FloWaveNet.reverse_sharded
+    again = net.reverse_chunk(z[:, :mid + halo].contiguous().cuda(), c[:, :(mid + halo) // 4].contiguous().cuda(), 0, halo)
+    assert torch.equal(again, outs[0])

@@ -394,6 +394,23 @@ class FloWaveNet:
             x, c, _ = block.reverse(x, c, None)
         return x
 
+    def reverse_chunk(self, z_ext, c_ext, halo_l, halo_r):
+        """Inverse pass of a time chunk extended by real neighbour data (fwn_reverse_chunk); returns the interior."""
+        z, c = self._check_xc(z_ext, c_ext, "z")
+        self._sync_params()
+        B, Te = z.shape[0], z.shape[1]
+        ws = self._workspace(B, Te)
+        x = torch.empty(B, Te - halo_l - halo_r, 1, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().fwn_reverse_chunk(self._h, _lib.ptr(z), _lib.ptr(c), B, Te, int(halo_l), int(halo_r), _lib.ptr(x),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return x
+
+    def reverse_sharded(self, z_local, c_local, rank, world, group=None):
+        """Time-chunk sharded synthesis of one long utterance (see sharding.py)."""
+        from . import sharding
+        return sharding.reverse_sharded(self.reverse_chunk, self._hparams, z_local, c_local, rank, world, group)
+
     def receptive_halo(self):
         return _lib.lib().fwn_receptive_halo(self._h)
 
