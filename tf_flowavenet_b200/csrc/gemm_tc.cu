@@ -13,9 +13,11 @@
 // * Epilogue warps read TMEM with tcgen05.ld (each thread owns one output row) and apply the fused flow op:
 //   tanh*sigmoid gate, residual + skip accumulation, bias+ReLU, or ActNorm + affine coupling + log-det in place on x.
 // Persistent grid (<= one CTA per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-9 epilogue (two warps per TMEM lane group, each owning half of the tile's columns; the residual / skip
-// inputs of a tile are prefetched into registers before the accumulator is waited for, so their HBM latency is hidden).
+// warps 2-9 epilogue: two groups of four warps (one per TMEM lane group) that ALTERNATE tiles, each group owning one TMEM
+// accumulator stage and one staging buffer, so the latency chains of two consecutive tiles overlap.  Tiles move through
+// 128B-swizzled shared memory: residual / skip inputs arrive by TMA bulk loads, outputs leave by per-warp TMA bulk stores.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "model.h"
@@ -40,6 +42,7 @@ struct alignas(64) TcArgs {
   int last_ksteps[MAX_SEG];  // valid 16-wide MMA steps in the segment's last chunk (1..4)
   int wk0[MAX_SEG];          // first W column (k) of the segment
   int nseg;
+  int multicast;             // weight map has (64, BN/2) boxes and the kernel runs as cta_group::2 CTA pairs
   int B, Ti, tiles_per_utt, n_tiles, N;
   EpiArgs e;
 };
@@ -91,6 +94,70 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(smem)),
                "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants.  Both CTAs issue their own loads into their own shared memory, but the
+// transaction bytes complete on the LEADER's (even CTA's) barrier: clearing bit 24 of a shared::cluster address selects
+// the even CTA of the pair at the same offset.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= [A0;A1] * [B0;B1]^T : M=256 across the pair, issued by the leader CTA only
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all previously issued pair-MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// plain arrive on the barrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -170,24 +237,33 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
 // WS (weight-stationary): the CTA owns ONE column tile for its whole life; that tile's weights (K <= 256, i.e. <= 4
 // chunks) are loaded once into shared memory and only activations stream through the (A-only, deeper) pipeline.
 // Used by the K=256 1x1 GEMMs (res|skip, final) whose per-tile weight traffic otherwise dwarfs their MMA time.
-template <int EPI, int BN, bool WS>
+// PAIR: CTAs are launched as 2-CTA clusters (one SM pair) working on two neighbouring row tiles of the SAME column tile
+// with ONE tcgen05.mma.cta_group::2 (M=256): each CTA stages its own A tile and only HALF of the weight box, which halves
+// both the L2->SM weight traffic and -- the actual limiter of the single-CTA kernel -- the shared-memory bandwidth per MMA
+// (TMA fill + operand read drop from 192 to 128 bytes per cycle per SM).
+template <int EPI, int BN, bool WS, bool PAIR = false>
 struct Cfg {
   static constexpr bool STAGED = (EPI == EPI_GATE) || (EPI == EPI_RES_SKIP) || (EPI == EPI_PLAIN && BN >= 128);
   static constexpr bool IN_PLACE = (EPI == EPI_RES_SKIP);                 // staging tile is TMA-loaded, updated in place, TMA-stored
   static constexpr int OUT_COLS = (EPI == EPI_GATE) ? BN / 2 : BN;        // bf16 output columns per tile
   static constexpr int SUBTILES = STAGED ? OUT_COLS / 64 : 0;             // [128 rows x 64 cols] 16 KB boxes
   static constexpr int STG_BYTES = SUBTILES * BM * 128;
-  // staging ring depth: in-place tiles need 3 so the input load of tile i+2 is issued while tile i+1 is processed;
-  // plain staged stores use 2 when shared memory allows (WS), so a tile never waits for the store issued just before it
-  static constexpr int NSTG = STAGED ? (IN_PLACE ? 3 : (WS ? 2 : 1)) : 0;
-  static constexpr int B_BYTES = BN * BK * 2;
+  // staging buffers: one per epilogue group (the two groups of four warps alternate tiles); in-place tiles use a ring of 3
+  // so a buffer is refilled a full tile after the group that stored from it moved on (lazy release, nobody waits on a
+  // store it just issued)
+  static constexpr int NSTG = STAGED ? (IN_PLACE ? 3 : 2) : 0;
+  // epilogue organisation: 2 = two groups of four warps alternate tiles (short, latency-bound tiles);
+  //                        1 = all eight warps share every tile, splitting its columns (long MMA-bound gate tiles)
+  static constexpr int GROUPS = (EPI == EPI_GATE) ? 1 : 2;
+  static constexpr int BIAS_BYTES = WS ? BN * 4 : 0;   // weight-stationary CTAs keep their column tile's bias in smem
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // per-CTA share of the weight box
   static constexpr int WS_CHUNKS = 4;
   static constexpr int W_BYTES = WS ? WS_CHUNKS * B_BYTES : 0;
   static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
   static constexpr int BUDGET = 225 * 1024 - NSTG * STG_BYTES - W_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + BIAS_BYTES + 256;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -201,13 +277,24 @@ __device__ __forceinline__ uint32_t stg_off(int r, int c) {
 // `stg` = this tile's staging buffer (STAGED kinds); for RES_SKIP it already holds the residual input / running skip sum.
 template <int EPI, int BN, bool WS>
 __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool row_ok, int r, int n_tile, int c0, const uint32_t* v,
-                                           uint8_t* stg, bool have_in, double& ls_sum) {
-  using C = Cfg<EPI, BN, WS>;
+                                           uint8_t* stg, bool have_in, const float* sbias, double& ls_sum) {
+  using C = Cfg<EPI, BN, WS, false>;
   const EpiArgs& e = a.e;
   const int col = n_tile * BN + c0;  // global column of v[0]
   float acc[16];
+  if (WS) {  // this CTA's column tile never changes: bias staged once in shared memory (broadcast 128-bit reads)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + ((col + j < a.N) ? __ldg(e.bias + col + j) : 0.f);
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+      acc[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+      acc[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+      acc[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+      acc[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + ((col + j < a.N) ? __ldg(e.bias + col + j) : 0.f);
+  }
   if (EPI == EPI_GATE) {
     // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124); 16 columns -> 8 channels = one 16-byte chunk
     uint32_t p[4];
@@ -299,15 +386,17 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int EPI, int BN, bool WS>
+template <int EPI, int BN, bool WS, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcArgs a) {
-  using C = Cfg<EPI, BN, WS>;
+  using C = Cfg<EPI, BN, WS, PAIR>;
+  static_assert(!(WS && PAIR), "the CTA-pair variant is for the streaming kernel");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* w_base = smem + (size_t)C::STAGES * C::STAGE_BYTES;   // WS: resident weight chunks
   uint8_t* stg_base = w_base + C::W_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (size_t)C::NSTG * C::STG_BYTES);
+  float* sbias = reinterpret_cast<float*>(stg_base + (size_t)C::NSTG * C::STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + C::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -323,7 +412,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   const int ws_groups = WS ? (int)gridDim.x / a.n_tiles : 1;
   const int ws_n = WS ? (int)blockIdx.x % a.n_tiles : 0;
   const int ws_m0 = WS ? (int)blockIdx.x / a.n_tiles : 0;
+  const int mc_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = mc_rank == 0;
   auto tile_of = [&](int it, int& m_tile, int& n_tile) -> bool {
+    if (PAIR) {  // cluster c handles row-tile pairs; an odd tail pair's second tile is a dummy (TMA zero fill in, clipped out)
+      const int p = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
+      const int m_pair = p / a.n_tiles;
+      n_tile = p - m_pair * a.n_tiles;
+      m_tile = 2 * m_pair + mc_rank;
+      return m_pair < (num_m_tiles + 1) / 2;
+    }
     if (WS) {
       m_tile = ws_m0 + it * ws_groups;
       n_tile = ws_n;
@@ -344,18 +442,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, EPI_THREADS);
+      mbar_init(tmem_empty + i, (C::GROUPS == 2 ? 4 : 8) * (PAIR ? 2 : 1));   // one arrive per warp draining this stage
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(in_full + i, 1);
-      mbar_init(in_empty + i, 1);
+      mbar_init(in_empty + i, 4);   // the four warps of the group that stored from this staging buffer
     }
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  if (WS) {
+    for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {
+      const int col = ws_n * BN + i;
+      sbias[i] = col < a.N ? __ldg(a.e.bias + col) : 0.f;
+    }
+  }
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm<C::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // peer barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -386,8 +494,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
         if (C::IN_PLACE) {
           // epilogue input tile -> staging buffer it % NSTG; the buffer is free once the TMA store that last used it has read it
-          const int b = it % C::NSTG;
-          mbar_wait(in_empty + b, ((it / C::NSTG) & 1) ^ 1);
+          const int b = it % 3;
+          mbar_wait(in_empty + b, ((it / 3) & 1) ^ 1);
           const int im = input_map_of(n_tile);
           if (im >= 0) {
             const int cin0 = (n_tile * BN) % a.e.F;  // column of this tile inside the [rows, F] input tensor
@@ -403,9 +511,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           for (int ch = 0; ch < a.nchunk[s]; ++ch) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * C::STAGE_BYTES;
-            mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
-            tma_load_3d(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
-            if (!WS) tma_load_2d(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN);
+            if (PAIR) {
+              // both CTAs' loads complete on the leader's full barrier, which therefore expects both shares
+              if (leader) mbar_expect_tx(full_bar + stage, 2 * C::STAGE_BYTES);
+              tma_load_3d_2sm(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
+              tma_load_2d_2sm(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN + mc_rank * (BN / 2));
+            } else {
+              mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
+              tma_load_3d(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
+              if (!WS) tma_load_2d(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN);
+            }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -413,7 +528,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc<BN>();
+    constexpr uint32_t idesc = PAIR ? (make_idesc<BN>() & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24) : make_idesc<BN>();
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
     int m_tile, n_tile;
@@ -421,7 +536,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       mbar_wait(w_full, 0);
       tcgen05_fence_after();
     }
-    for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
+    for (int it = 0; leader && tile_of(it, m_tile, n_tile); ++it) {   // in a pair only the leader CTA issues MMAs
       mbar_wait(tmem_empty + as, aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -438,91 +553,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             const int ksteps = (ch == a.nchunk[s] - 1) ? a.last_ksteps[s] : BK / UMMA_K;
             for (int k = 0; k < ksteps; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte address units
-              umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+              if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+              else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
+            if (PAIR) umma_commit_2sm(empty_bar + stage);  // release the stage in both CTAs
+            else umma_commit(empty_bar + stage);           // frees the smem stage once these MMAs have read it
           }
           accumulate = 1;
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (lane == 0) umma_commit(tmem_full + as);  // accumulator complete -> epilogue
+      if (lane == 0) {                             // accumulator complete -> epilogue (of both CTAs for a pair)
+        if (PAIR) umma_commit_2sm(tmem_full + as);
+        else umma_commit(tmem_full + as);
+      }
       __syncwarp();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    const int lg = warp & 3;              // TMEM lane group this warp may access
-    const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp owns
+    // ===================== epilogue (warps 2..9): two groups of four warps alternate tiles =====================
+    const int lg = warp & 3;            // TMEM lane group this warp may access
+    const int grp = C::GROUPS == 2 ? (warp - 2) >> 2 : 0;    // GROUPS==2: group g drains TMEM stage g (tiles it % 2 == g)
+    const int half = C::GROUPS == 1 ? (warp - 2) >> 2 : 0;   // GROUPS==1: which half of every tile's columns this warp owns
+    constexpr int CWID = C::GROUPS == 1 ? BN / 2 : BN;       // accumulator columns per warp
+    const int cbeg = half * CWID;
     const int r = lg * 32 + lane;
-    constexpr int CW = BN >= 32 ? BN / 2 : BN;  // accumulator columns per warp
-    const bool active = (BN >= 32) || half == 0;
-    const int cbeg = half * CW;
-    const bool elected = (threadIdx.x == 64);   // first epilogue thread issues the TMA stores
-    int as = 0;
-    uint32_t aphase = 0;
     double ls_sum = 0.0;
     int m_tile, n_tile;
-    for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
+    for (int it = grp; tile_of(it, m_tile, n_tile); it += C::GROUPS) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1;
       const int ub = m_tile / a.tiles_per_utt;
       const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
       const int t = t0 + r;
-      const bool row_ok = t < a.Ti;
+      const bool row_ok = t < a.Ti && ub < a.B;
       const int64_t row = (int64_t)ub * a.Ti + t;
-      const int b = C::STAGED ? it % C::NSTG : 0;
-      uint8_t* stg = stg_base + (size_t)b * C::STG_BYTES;
+      const int sb = C::IN_PLACE ? it % 3 : as;
+      uint8_t* stg = stg_base + (size_t)sb * C::STG_BYTES;
       bool have_in = false;
-      if (C::STAGED && !C::IN_PLACE) {
-        // the store that last used this staging buffer (NSTG tiles ago) must have finished READING it before we overwrite it
-        if (elected) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::NSTG > 0 ? C::NSTG - 1 : 0) : "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (C::STAGED) {
+        // the store this warp issued from this staging slice (tile it-2) has had a whole tile to read it
+        if (lane == 0) {
+          if (C::GROUPS == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (C::IN_PLACE && it >= 2) mbar_arrive(in_empty + ((it - 2) % 3));   // lazy release -> input of tile it+1 may land there
+        }
+        __syncwarp();
       }
       if (C::IN_PLACE) {
         have_in = input_map_of(n_tile) >= 0;
-        mbar_wait(in_full + b, (it / C::NSTG) & 1);
+        mbar_wait(in_full + sb, (uint32_t)(it / 3) & 1);
       }
       mbar_wait(tmem_full + as, aphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cbeg);
-      if (active) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
+      constexpr int LDW = CWID >= 64 ? 64 : CWID;   // accumulator columns fetched per tcgen05.wait::ld
 #pragma unroll
-        for (int cc = 0; cc < CW; cc += 32) {
-          uint32_t v[32];
-          tmem_ld_x16(taddr + cc, v);
-          if (CW > 16) tmem_ld_x16(taddr + cc + 16, v + 16);
-          tmem_ld_wait();
-          epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cbeg + cc, v, stg, have_in, ls_sum);
-          if (CW > 16) epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cbeg + cc + 16, v + 16, stg, have_in, ls_sum);
-        }
+      for (int cc = cbeg; cc < cbeg + CWID; cc += LDW) {
+        uint32_t v[LDW];
+#pragma unroll
+        for (int j = 0; j < LDW; j += 16) tmem_ld_x16(taddr + cc + j, v + j);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < LDW; j += 16) epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cc + j, v + j, stg, have_in, sbias, ls_sum);
       }
       tcgen05_fence_before();
-      mbar_arrive(tmem_empty + as);   // accumulator drained: the MMA warp may start tile it+2 in this TMEM stage
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      __syncwarp();
+      if (lane == 0) {                // accumulator drained: the (leader's) MMA warp may start tile it+2 in this TMEM stage
+        if (PAIR) mbar_arrive_remote(tmem_empty + as, 0);
+        else mbar_arrive(tmem_empty + as);
+      }
       if (C::STAGED) {
-        // generic-proxy writes -> visible to the async proxy, then one thread issues the bulk stores (rows >= Ti are clipped by TMA)
+        // generic-proxy writes -> visible to the async proxy; then this warp stores its own 32 rows (rows >= Ti are clipped)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
-        if (elected) {
+        __syncwarp();
+        if (lane == 0) {
           int om = 0, ocol = n_tile * C::OUT_COLS;
           if (EPI == EPI_RES_SKIP) {
             om = (a.e.has_res && n_tile * BN < a.e.F) ? 0 : 1;
             ocol = (n_tile * BN) % a.e.F;
           }
+          constexpr int SPW = C::SUBTILES / (C::GROUPS == 1 ? 2 : 1);   // 64-column sub-tiles per warp
 #pragma unroll
-          for (int j = 0; j < C::SUBTILES; ++j)
-            tma_store_3d(&a.mapOut[om], stg + (size_t)j * BM * 128, ocol + j * 64, t0, ub);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (C::IN_PLACE) {
-            // all but the newest store have read their staging buffer -> the buffer of tile it-1 may be refilled (for tile it+2)
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (it >= 1) mbar_arrive(in_empty + ((it - 1) % C::NSTG));
+          for (int jj = 0; jj < SPW; ++jj) {
+            const int j = half * SPW + jj;
+            tma_store_3d(&a.mapOut[om], stg + (size_t)j * BM * 128 + (size_t)lg * 32 * 128, ocol + j * 64, t0 + lg * 32, ub);
           }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
-    if (C::STAGED && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (C::STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (EPI == EPI_AFFINE) {
       if (!a.e.reverse && a.e.logdet_acc) {
         ls_sum = warp_sum(ls_sum);
@@ -532,9 +655,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer's MMAs / arrives may still target it
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -566,6 +691,20 @@ int make_act_map(CUtensorMap* map, const void* base, int B, int Ti, int C, int64
   FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations B=%d Ti=%d C=%d) failed: %d", B, Ti, C, (int)r);
   return 0;
 }
+// same tensor, (64, 32, 1) boxes: the per-warp TMA stores of the epilogue (one TMEM lane group = 32 rows)
+int make_store_map(CUtensorMap* map, const void* base, int B, int Ti, int C, int64_t ld) {
+  EncodeFn enc = get_encode();
+  FWN_CHECK(enc, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  FWN_CHECK((ld * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) % 16) == 0, "TMA needs 16-byte aligned rows (ld=%lld)", (long long)ld);
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Ti, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)Ti};
+  cuuint32_t box[3] = {BK, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store map B=%d Ti=%d C=%d) failed: %d", B, Ti, C, (int)r);
+  return 0;
+}
 // weights [Npad, Kpad] bf16 -> 2-D map, box (64, bn)
 int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
   EncodeFn enc = get_encode();
@@ -580,12 +719,12 @@ int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
   return 0;
 }
 
-template <int EPI, int BN, bool WS>
+template <int EPI, int BN, bool WS, bool PAIR = false>
 static int launch(const TcArgs& a, cudaStream_t st) {
-  using C = Cfg<EPI, BN, WS>;
+  using C = Cfg<EPI, BN, WS, PAIR>;
   static bool configured = false;
   if (!configured) {
-    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, WS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
   const int num_m = a.B * a.tiles_per_utt;
@@ -596,10 +735,29 @@ static int launch(const TcArgs& a, cudaStream_t st) {
     FWN_CHECK(nch <= C::WS_CHUNKS, "weight-stationary GEMM needs K <= 256");
     const int groups = std::max(1, std::min(num_m, num_sms() / a.n_tiles));
     grid = groups * a.n_tiles;
+  } else if (PAIR) {
+    const int pairs = ((num_m + 1) / 2) * a.n_tiles;
+    grid = 2 * std::min(pairs, num_sms() / 2);
   } else {
     grid = std::min(num_m * a.n_tiles, num_sms());
   }
-  tc_gemm_kernel<EPI, BN, WS><<<grid, NUM_THREADS, C::SMEM, st>>>(a);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FWN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, WS, PAIR>, a));
+  } else {
+    tc_gemm_kernel<EPI, BN, WS, PAIR><<<grid, NUM_THREADS, C::SMEM, st>>>(a);
+  }
   FWN_LAUNCH_CHECK();
   return 0;
 }
@@ -617,7 +775,9 @@ int block_n_for(EpiKind kind, int N, bool model_path) {
 int tc_launch(TcArgs& a, EpiKind kind, int bn, bool ws, cudaStream_t st) {
   FWN_CHECK(a.n_tiles * bn <= 512, "tc_gemm: N=%d too wide", a.N);
   switch (kind) {
-    case EPI_GATE: FWN_CHECK(bn == 256, "gate needs BN=256"); return launch<EPI_GATE, 256, false>(a, st);
+    case EPI_GATE:
+      FWN_CHECK(bn == 256, "gate needs BN=256");
+      return a.multicast ? launch<EPI_GATE, 256, false, true>(a, st) : launch<EPI_GATE, 256, false, false>(a, st);
     case EPI_RES_SKIP: FWN_CHECK(bn == 128 && ws, "res/skip runs weight-stationary at BN=128"); return launch<EPI_RES_SKIP, 128, true>(a, st);
     case EPI_PLAIN:
       if (ws) { FWN_CHECK(bn == 128, "weight-stationary plain GEMM needs BN=128"); return launch<EPI_PLAIN, 128, true>(a, st); }
@@ -643,12 +803,24 @@ int tc_launch(TcArgs& a, EpiKind kind, int bn, bool ws, cudaStream_t st) {
 }  // namespace tc
 
 // ---------------------------------------------------------------- engine glue
+// FWN_GATE_PAIR=0 runs the gate GEMM as single-CTA MMAs instead of cta_group::2 pairs (diagnostics / A-B timing)
+static bool gate_multicast() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_GATE_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 struct TcPlan {
   Workspace w;
-  // activation maps per block: h0, h1, o, s, u (C = F) and cA, cB (C = Kc)
-  std::vector<CUtensorMap> act;  // [n_block * 7]
+  // activation maps per block: h0, h1, o, s, u (C = F), cA, cB (C = Kc) and a0 (C = ceil8(nq))
+  std::vector<CUtensorMap> act;  // [n_block * 8]
+  std::vector<CUtensorMap> st32; // [n_block * 5] store maps (32-row boxes) of h0, h1, o, s, u
   std::vector<CUtensorMap> wmap; // [n_flows * GEMM_IDS]
   std::vector<int> wbn;          // BN each weight map was built for
+  std::vector<char> wws;         // runs weight-stationary
 };
 
 static int act_index(const Workspace& w, const void* p) {
@@ -659,6 +831,7 @@ static int act_index(const Workspace& w, const void* p) {
   if (p == w.u) return 4;
   if (p == w.cA) return 5;
   if (p == w.cB) return 6;
+  if (p == w.a0) return 7;
   return -1;
 }
 
@@ -669,30 +842,39 @@ int tc_prepare(Model* m, const Workspace& w, int B, int T, cudaStream_t st) {
   if (!m->tc) m->tc = new TcPlan();
   TcPlan* p = m->tc;
   p->w = w;
-  p->act.assign((size_t)c.n_block * 7, CUtensorMap());
+  p->act.assign((size_t)c.n_block * 8, CUtensorMap());
+  p->st32.assign((size_t)c.n_block * 5, CUtensorMap());
   p->wmap.assign(m->flows.size() * GEMM_IDS, CUtensorMap());
   p->wbn.assign(m->flows.size() * GEMM_IDS, 0);
+  p->wws.assign(m->flows.size() * GEMM_IDS, 0);
   for (int i = 0; i < c.n_block; ++i) {
     const int Ti = T >> (i + 1), Kc = H << (i + 1);
-    void* bufs[7] = {w.h0, w.h1, w.o, w.s, w.u, w.cA, w.cB};
-    for (int k = 0; k < 7; ++k) {
-      const int C = k < 5 ? F : Kc;
-      if (tc::make_act_map(&p->act[(size_t)i * 7 + k], bufs[k], B, Ti, C, C)) return 1;
+    void* bufs[8] = {w.h0, w.h1, w.o, w.s, w.u, w.cA, w.cB, w.a0};
+    const int kq = ((1 << i) + 7) / 8 * 8;  // nq = 2^i pass-through channels, row pitch padded to 8
+    for (int k = 0; k < 8; ++k) {
+      const int C = k < 5 ? F : (k < 7 ? Kc : kq);
+      if (tc::make_act_map(&p->act[(size_t)i * 8 + k], bufs[k], B, Ti, C, C)) return 1;
+      if (k < 5 && tc::make_store_map(&p->st32[(size_t)i * 5 + k], bufs[k], B, Ti, C, C)) return 1;
     }
   }
   for (size_t f = 0; f < m->flows.size(); ++f) {
     const FlowPack& fp = m->flows[f];
-    auto mk = [&](int id, const void* wptr, int N, int Kpad, EpiKind kind) {
-      const int bn = tc::block_n_for(kind, N, true);
+    auto mk = [&](int id, const void* wptr, int N, int Kpad, EpiKind kind, int chunks = 4) {
+      // the 1x1 / front GEMMs run weight-stationary at BN=128 when their K fits 4 resident chunks, else streaming at BN=256
+      const bool ws = (kind == EPI_RES_SKIP || kind == EPI_PLAIN) && chunks <= 4;
+      const int bn = (kind == EPI_PLAIN && !ws) ? 256 : tc::block_n_for(kind, N, true);
+      p->wws[f * GEMM_IDS + id] = ws ? 1 : 0;
       const int Npad = (N + 15) / 16 * 16;
       p->wbn[f * GEMM_IDS + id] = bn;
-      return tc::make_w_map(&p->wmap[f * GEMM_IDS + id], wptr, Npad, Kpad, std::min(bn, Npad));
+      const int box = (kind == EPI_GATE && gate_multicast()) ? bn / 2 : std::min(bn, Npad);
+      return tc::make_w_map(&p->wmap[f * GEMM_IDS + id], wptr, Npad, Kpad, box);
     };
     for (int n = 0; n < L; ++n) {
       if (mk(GEMM_GATE0 + n, fp.gate_w[n], 2 * F, fp.gate_ld, EPI_GATE)) return 1;
       if (mk(GEMM_RS0 + n, fp.rs_w[n], n == L - 1 ? F : 2 * F, fp.rs_ld[n], EPI_RES_SKIP)) return 1;
     }
     if (mk(GEMM_FINAL, fp.final_w, F, fp.final_ld, EPI_PLAIN)) return 1;
+    if (mk(GEMM_FRONT, fp.front_wtc, F, fp.front_ld, EPI_PLAIN, 3 * ((fp.front_k16 + 63) / 64))) return 1;
     if (mk(GEMM_ZERO, fp.zero_w, 2 * fp.nq, fp.zero_ld, EPI_AFFINE)) return 1;
   }
   m->plan_B = B;
@@ -712,7 +894,7 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   for (int s = 0; s < g.nseg; ++s) {
     const int ai = act_index(p->w, g.seg[s].A);
     FWN_CHECK(ai >= 0, "tc_run: segment %d does not read a planned workspace buffer", s);
-    a.mapA[s] = p->act[(size_t)block * 7 + ai];
+    a.mapA[s] = p->act[(size_t)block * 8 + ai];
     a.shift[s] = g.seg[s].shift;
     const int K16 = (g.seg[s].K + 15) / 16 * 16;
     a.nchunk[s] = (K16 + tc::BK - 1) / tc::BK;
@@ -723,20 +905,26 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   auto act_map = [&](const void* ptr, CUtensorMap* dst) -> bool {
     const int ai = ptr ? act_index(p->w, ptr) : -1;
     if (ai < 0) return false;
-    *dst = p->act[(size_t)block * 7 + ai];
+    *dst = p->act[(size_t)block * 8 + ai];
+    return true;
+  };
+  auto store_map = [&](const void* ptr, CUtensorMap* dst) -> bool {
+    const int ai = ptr ? act_index(p->w, ptr) : -1;
+    if (ai < 0 || ai >= 5) return false;
+    *dst = p->st32[(size_t)block * 5 + ai];
     return true;
   };
   if (kind == EPI_GATE) {
-    FWN_CHECK(act_map(g.e.out0, &a.mapOut[0]), "tc_run: gate output is not a planned buffer");
+    FWN_CHECK(store_map(g.e.out0, &a.mapOut[0]), "tc_run: gate output is not a planned buffer");
   } else if (kind == EPI_RES_SKIP) {
     if (g.e.has_res) {
-      FWN_CHECK(act_map(g.e.out0, &a.mapOut[0]) && act_map(g.e.in0, &a.mapIn[0]), "tc_run: residual buffers are not planned buffers");
+      FWN_CHECK(store_map(g.e.out0, &a.mapOut[0]) && act_map(g.e.in0, &a.mapIn[0]), "tc_run: residual buffers are not planned buffers");
       a.has_in[0] = 1;
     }
-    FWN_CHECK(act_map(g.e.out1, &a.mapOut[1]), "tc_run: skip output is not a planned buffer");
+    FWN_CHECK(store_map(g.e.out1, &a.mapOut[1]), "tc_run: skip output is not a planned buffer");
     a.has_in[1] = act_map(g.e.in1, &a.mapIn[1]) ? 1 : 0;
   } else if (kind == EPI_PLAIN) {
-    FWN_CHECK(act_map(g.e.out0, &a.mapOut[0]), "tc_run: output is not a planned buffer");
+    FWN_CHECK(store_map(g.e.out0, &a.mapOut[0]), "tc_run: output is not a planned buffer");
   }
   const int bn = p->wbn[f * GEMM_IDS + gemm_id];
   a.B = g.B;
@@ -745,7 +933,8 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   a.N = g.N;
   a.n_tiles = (g.N + bn - 1) / bn;
   a.e = g.e;
-  const bool ws = (kind == EPI_RES_SKIP) || (kind == EPI_PLAIN);
+  const bool ws = p->wws[f * GEMM_IDS + gemm_id] != 0;
+  a.multicast = (kind == EPI_GATE && gate_multicast()) ? 1 : 0;
   return tc::tc_launch(a, kind, bn, ws, st);
 }
 
@@ -770,7 +959,7 @@ int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, i
   if (tc::make_w_map(&a.mapB, w, Npad, Kpad, std::min(bn, Npad))) return 1;
   a.B = B; a.Ti = T; a.tiles_per_utt = (T + tc::BM - 1) / tc::BM; a.N = Cout; a.n_tiles = (Cout + bn - 1) / bn;
   a.e.bias = bias; a.e.out0 = y; a.e.ld = Cout; a.e.relu = relu; a.e.F = Cout;
-  if (bn >= 128 && tc::make_act_map(&a.mapOut[0], y, B, T, Cout, Cout)) return 1;  // staged TMA-store epilogue
+  if (bn >= 128 && tc::make_store_map(&a.mapOut[0], y, B, T, Cout, Cout)) return 1;  // staged TMA-store epilogue
   return tc::tc_launch(a, EPI_PLAIN, bn, false, st);
 }
 

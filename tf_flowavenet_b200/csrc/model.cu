@@ -225,7 +225,7 @@ int model_prepack(Model* m, cudaStream_t st) {
 
   Bump b;
   struct FlowOff {  // offsets into the staging buffer, turned into device pointers after upload
-    size_t a_off, b_off, off2log, an_b, an_s, an_is, front_w, front_b, final_w, final_b, zero_w, zero_b;
+    size_t a_off, b_off, off2log, an_b, an_s, an_is, front_w, front_b, front_wtc, final_w, final_b, zero_w, zero_b;
     std::vector<size_t> gate_w, gate_b, rs_w, rs_b;
   };
   std::vector<FlowOff> offs;
@@ -311,6 +311,18 @@ int model_prepack(Model* m, cudaStream_t st) {
       {
         std::vector<double> w = wn_kernel(hp, wpre + "/Conv_front/conv1d", 3, nq, F);
         fo.front_w = store_floats(b, w);
+        fo.front_wtc = 0;
+        if (bf16) {  // tensor-core layout: [3*k16][F] with tap k at rows k*k16 .. k*k16+nq, then transposed to [F][Kpad]
+          const int k16 = (nq + 15) / 16 * 16;
+          std::vector<double> wt((size_t)3 * k16 * F, 0.0);
+          for (int k = 0; k < 3; ++k)
+            for (int q = 0; q < nq; ++q)
+              for (int ch = 0; ch < F; ++ch) wt[((size_t)k * k16 + q) * F + ch] = w[((size_t)k * nq + q) * F + ch];
+          int ld;
+          fo.front_wtc = store_matrix(b, wt, 3 * k16, F, true, &ld);
+          fp.front_ld = ld;
+          fp.front_k16 = k16;
+        }
         const float* bb = hp.p(wpre + "/Conv_front/conv1d/bias");
         fo.front_b = store_floats(b, std::vector<double>(bb, bb + F));
       }
@@ -437,6 +449,7 @@ int model_prepack(Model* m, cudaStream_t st) {
     fp.an_is = reinterpret_cast<float*>(base + fo.an_is);
     fp.front_w = reinterpret_cast<float*>(base + fo.front_w);
     fp.front_b = reinterpret_cast<float*>(base + fo.front_b);
+    fp.front_wtc = bf16 ? base + fo.front_wtc : nullptr;
     fp.final_w = base + fo.final_w;
     fp.final_b = reinterpret_cast<float*>(base + fo.final_b);
     fp.zero_w = base + fo.zero_w;
@@ -519,6 +532,7 @@ int model_plan(const Model* m, int B, int T, Workspace* w, char* base) {
   w->o = take(M0 * F * as);
   w->s = take(M0 * F * as);
   w->u = take(M0 * F * as);
+  w->a0 = take(c.precision == FWN_MIXED_BF16 ? (size_t)B * T * 8 : 0);  // rows_i * ceil8(nq_i) * 2 bytes <= 8*B*T
   w->bytes = off;
   return 0;
 }
@@ -639,8 +653,22 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   for (int k = 0; k < 3; ++k) fa.shift[k] = shift_of(k, 1);
   const double rows = (double)B * Ti;
   prof_begin(m, PROF_FRONT, 2.0 * rows * 3 * fp.nq * F, st);
-  m->launches++;
-  if (front_conv(fa, bf16, st)) return 1;
+  if (!bf16) {
+    m->launches++;
+    if (front_conv(fa, false, st)) return 1;
+  } else {
+    // mixed mode: tiny gather/cast kernel, then the front conv is three time-shifted K segments on the tcgen05 engine
+    const int kq = (fp.nq + 7) / 8 * 8;
+    m->launches++;
+    if (front_pack(X, fp.Cx, fp.nq, kq, fp.off2log, fa.an_b, fa.an_s, w.a0, (int64_t)B * Ti, st)) return 1;
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    for (int k = 0; k < 3; ++k) g.seg[k] = Seg{w.a0, kq, fa.shift[k], fp.nq, k * fp.front_k16};
+    g.nseg = 3;
+    g.W = fp.front_wtc; g.ldw = fp.front_ld; g.N = F;
+    g.e.bias = fp.front_b; g.e.out0 = w.h0; g.e.ld = F; g.e.relu = 1; g.e.F = F;
+    if (run_gemm(m, g, EPI_PLAIN, GEMM_FRONT, fp, st)) return 1;
+  }
   prof_end(m, st);
 
   void* hin = w.h0;

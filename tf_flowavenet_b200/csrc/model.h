@@ -28,6 +28,8 @@ struct FlowPack {
   float *an_b, *an_s, *an_is;      // ActNorm bias / exp(3 logs) / exp(-3 logs), physical order
   float *raw_b, *raw_logs;         // the reference-named variables (updated by DDI)
   float *front_w, *front_b;
+  void* front_wtc;   // mixed mode: bf16 [F][Kpad], K index = tap*ceil16(nq) + q (tcgen05 B operand)
+  int front_ld, front_k16;  // Kpad and ceil16(nq)
   void* gate_w[MAX_LAYERS]; float* gate_b[MAX_LAYERS];
   void* rs_w[MAX_LAYERS];   float* rs_b[MAX_LAYERS];
   void* final_w; float* final_b;
@@ -41,10 +43,12 @@ struct Workspace {
   float* x;
   float* up[2];
   void *cA, *cB, *h0, *h1, *o, *s, *u;
+  void* a0;       // mixed mode: bf16 [rows, ceil8(nq)] ActNorm'd pass-through half of x (A operand of the front conv)
   size_t bytes;
 };
 
-enum GemmId { GEMM_GATE0 = 0, GEMM_RS0 = MAX_LAYERS, GEMM_FINAL = 2 * MAX_LAYERS, GEMM_ZERO = 2 * MAX_LAYERS + 1, GEMM_IDS = 2 * MAX_LAYERS + 2 };
+enum GemmId { GEMM_GATE0 = 0, GEMM_RS0 = MAX_LAYERS, GEMM_FINAL = 2 * MAX_LAYERS, GEMM_ZERO = 2 * MAX_LAYERS + 1, GEMM_FRONT = 2 * MAX_LAYERS + 2,
+              GEMM_IDS = 2 * MAX_LAYERS + 3 };
 
 struct TcPlan;  // tensor maps of the tcgen05 engine (gemm_tc.cu)
 
