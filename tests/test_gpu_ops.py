@@ -17,7 +17,7 @@ def rnd(*shape, seed=0, scale=1.0):
     return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape) * scale).float()
 
 
-@pytest.mark.parametrize("B,T,C", [(1, 2, 1), (2, 64, 1), (3, 34, 4), (1, 4096, 80), (2, 10, 160)])
+@pytest.mark.parametrize("B,T,C", [(1, 2, 1), (2, 64, 1), (3, 34, 2), (3, 34, 4), (5, 6, 3), (1, 4096, 80), (2, 10, 160), (1, 8, 6)])
 def test_squeeze_unsqueeze_bit_exact(B, T, C):
     from tf_flowavenet_b200.model import _squeeze
     x = rnd(B, T, C, seed=1)

@@ -33,11 +33,47 @@ __global__ void squeeze_kernel(const float* __restrict__ x, float* __restrict__ 
   }
 }
 
+// 128-bit variant (C % 4 == 0): one thread moves 8 floats of one 2C-float group.
+//   squeeze:   a = in[c0..c0+3] (row parity 0), b = in[C+c0..] (parity 1)  ->  out[2c0..2c0+7] = a0 b0 a1 b1 a2 b2 a3 b3
+//   unsqueeze: the inverse de-interleave.
+template <bool INVERSE>
+__global__ void squeeze_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n8, int C) {
+  const int q = C / 4;  // float4 per half group
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t grp = i / q;
+    const int c4 = (int)(i - grp * q);
+    const int64_t base = grp * 2 * q;  // float4 index of the group's first element
+    if (!INVERSE) {
+      const float4 a = __ldg(x + base + c4), b = __ldg(x + base + q + c4);
+      y[base + 2 * c4] = make_float4(a.x, b.x, a.y, b.y);
+      y[base + 2 * c4 + 1] = make_float4(a.z, b.z, a.w, b.w);
+    } else {
+      const float4 u = __ldg(x + base + 2 * c4), v = __ldg(x + base + 2 * c4 + 1);
+      y[base + c4] = make_float4(u.x, u.z, v.x, v.z);
+      y[base + q + c4] = make_float4(u.y, u.w, v.y, v.w);
+    }
+  }
+}
+// C == 2: a group is one float4 (k0c0 k0c1 k1c0 k1c1) <-> (c0k0 c0k1 c1k0 c1k1): swap the middle pair (self-inverse)
+__global__ void squeeze_c2_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    y[i] = make_float4(v.x, v.z, v.y, v.w);
+  }
+}
+static bool aligned16(const void* a, const void* b) { return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0; }
+
 int squeeze(const float* x, float* y, int B, int T, int C, cudaStream_t st) {
   FWN_CHECK(T % 2 == 0, "squeeze: T=%d must be even (model.py:226)", T);
   int64_t n = (int64_t)B * T * C;
   if (n == 0) return 0;
-  squeeze_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C, false);
+  if (C == 1) {  // out[b,t,k] = x[b,2t+k,0]: the identity on memory
+    if (x != y) FWN_CUDA(cudaMemcpyAsync(y, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (C == 2 && aligned16(x, y)) squeeze_c2_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>((const float4*)x, (float4*)y, n / 4);
+  else if (C % 4 == 0 && aligned16(x, y)) squeeze_vec_kernel<false><<<ew_grid(n / 8, 256), 256, 0, st>>>((const float4*)x, (float4*)y, n / 8, C);
+  else squeeze_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C, false);
   FWN_LAUNCH_CHECK();
   return 0;
 }
@@ -45,7 +81,13 @@ int unsqueeze(const float* x, float* y, int B, int T, int C, cudaStream_t st) {
   FWN_CHECK(C % 2 == 0, "unsqueeze: C=%d must be even (model.py:260)", C);
   int64_t n = (int64_t)B * T * C;
   if (n == 0) return 0;
-  squeeze_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C / 2, true);
+  if (C == 2) {
+    if (x != y) FWN_CUDA(cudaMemcpyAsync(y, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (C == 4 && aligned16(x, y)) squeeze_c2_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>((const float4*)x, (float4*)y, n / 4);
+  else if ((C / 2) % 4 == 0 && aligned16(x, y)) squeeze_vec_kernel<true><<<ew_grid(n / 8, 256), 256, 0, st>>>((const float4*)x, (float4*)y, n / 8, C / 2);
+  else squeeze_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C / 2, true);
   FWN_LAUNCH_CHECK();
   return 0;
 }
@@ -58,10 +100,32 @@ __global__ void change_order_kernel(const float* __restrict__ x, float* __restri
     y[i] = __ldg(x + row * C + (c < h ? c + h : c - h));
   }
 }
+// 128-bit variant: C/2 % 4 == 0 -> whole float4s move; C == 2 / 4 -> swizzle inside one float4
+__global__ void change_order_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, int C) {
+  const int q = C / 4, hq = C / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    if (C == 2) {
+      const float4 v = __ldg(x + i);
+      y[i] = make_float4(v.y, v.x, v.w, v.z);
+    } else if (C == 4) {
+      const float4 v = __ldg(x + i);
+      y[i] = make_float4(v.z, v.w, v.x, v.y);
+    } else {
+      const int64_t row = i / q;
+      const int c4 = (int)(i - row * q);
+      y[i] = __ldg(x + row * q + (c4 < hq ? c4 + hq : c4 - hq));
+    }
+  }
+}
 int change_order(const float* x, float* y, int64_t rows, int C, cudaStream_t st) {
   FWN_CHECK(C % 2 == 0, "change_order: C=%d must be even", C);
   int64_t n = rows * C;
   if (n == 0) return 0;
+  if ((C == 2 || C == 4 || C % 8 == 0) && n % 4 == 0 && aligned16(x, y)) {
+    change_order_vec_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>((const float4*)x, (float4*)y, n / 4, C);
+    FWN_LAUNCH_CHECK();
+    return 0;
+  }
   change_order_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, y, n, C);
   FWN_LAUNCH_CHECK();
   return 0;
@@ -215,6 +279,40 @@ __global__ void affine_kernel(const float* __restrict__ x, const float* __restri
     if (threadIdx.x == 0) atomicAdd(acc, ls);
   }
 }
+// 128-bit variant of the affine coupling.  MODE 0: (C/2) % 4 == 0 (one float4 of the transformed half + the matching
+// pass-through float4 per thread); MODE 2: C == 2 (two rows per float4); MODE 4: C == 4 (one row per float4).
+template <bool REV, int MODE>
+__global__ void affine_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ net, float4* __restrict__ y, double* __restrict__ acc,
+                                  int64_t nwork, int C) {
+  __shared__ double red[32];
+  float ls = 0.f;
+  auto tr = [&](float v, float log_s, float t) -> float {
+    if (REV) return v * expf(log_s) + t;
+    ls += log_s;
+    return (v - t) * expf(-log_s);
+  };
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nwork; i += (int64_t)gridDim.x * blockDim.x) {
+    if (MODE == 2) {         // x = (a0 b0 a1 b1), net = (ls0 t0 ls1 t1)
+      const float4 v = __ldg(x + i), w = __ldg(net + i);
+      y[i] = make_float4(v.x, tr(v.y, w.x, w.y), v.z, tr(v.w, w.z, w.w));
+    } else if (MODE == 4) {  // x = (a0 a1 b0 b1), net = (ls0 ls1 t0 t1)
+      const float4 v = __ldg(x + i), w = __ldg(net + i);
+      y[i] = make_float4(v.x, v.y, tr(v.z, w.x, w.z), tr(v.w, w.y, w.w));
+    } else {
+      const int hq = C / 8, q = C / 4;  // float4 per half row / per row
+      const int64_t row = i / hq;
+      const int c4 = (int)(i - row * hq);
+      const float4 a = __ldg(x + row * q + c4), b = __ldg(x + row * q + hq + c4);
+      const float4 l = __ldg(net + row * q + c4), t = __ldg(net + row * q + hq + c4);
+      y[row * q + c4] = a;
+      y[row * q + hq + c4] = make_float4(tr(b.x, l.x, t.x), tr(b.y, l.y, t.y), tr(b.z, l.z, t.z), tr(b.w, l.w, t.w));
+    }
+  }
+  if (!REV && acc) {
+    double d = block_sum((double)ls, red);
+    if (threadIdx.x == 0) atomicAdd(acc, d);
+  }
+}
 __global__ void affine_logdet_finish(const double* acc, float* out, double denom) { *out = (float)(-(*acc) / denom / 2.0); }
 
 int affine(const float* x, const float* net, float* y, float* logdet_out, int64_t rows, int C, bool affine_, bool rev, double* scratch,
@@ -224,7 +322,18 @@ int affine(const float* x, const float* net, float* y, float* logdet_out, int64_
   if (n == 0) return 0;
   int grid = ew_grid(n, 256);
   if (scratch) FWN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
-  if (affine_) {
+  const int mode = C == 2 ? 2 : (C == 4 ? 4 : ((C / 2) % 4 == 0 ? 0 : -1));
+  const bool vec = affine_ && mode >= 0 && n % 4 == 0 && aligned16(x, y) && aligned16(net, net);
+  if (vec) {
+    const int64_t nwork = mode == 0 ? rows * (C / 8) : n / 4;
+    const int g2 = ew_grid(nwork, 256);
+    const float4 *x4 = (const float4*)x, *n4 = (const float4*)net;
+    float4* y4 = (float4*)y;
+#define FWN_AFF(R, M) affine_vec_kernel<R, M><<<g2, 256, 0, st>>>(x4, n4, y4, R ? nullptr : scratch, nwork, C)
+    if (rev) { if (mode == 2) FWN_AFF(true, 2); else if (mode == 4) FWN_AFF(true, 4); else FWN_AFF(true, 0); }
+    else { if (mode == 2) FWN_AFF(false, 2); else if (mode == 4) FWN_AFF(false, 4); else FWN_AFF(false, 0); }
+#undef FWN_AFF
+  } else if (affine_) {
     if (rev) affine_kernel<true, true><<<grid, 256, 0, st>>>(x, net, y, nullptr, rows, C);
     else affine_kernel<false, true><<<grid, 256, 0, st>>>(x, net, y, scratch, rows, C);
   } else {
@@ -342,53 +451,65 @@ __global__ void upsample_kernel(const float* __restrict__ in, const float* __res
     }
   }
 }
-// Vectorised variant for the fused path's split bf16/fp32 planes: one thread = 8 consecutive mel bins of one
-// output time step (requires mels/2 % 8 == 0): 2 x 10 input values, 48 FMA, one 16-byte (bf16) store.
-template <typename TOut>
-__global__ void upsample_split8_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias_p,
-                                       TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
-  extern __shared__ float sw[];
+// Warp-cooperative upsampler (mels % 16 == 0): one warp owns one input-frame pair (j0-1, j0) of one utterance and
+// produces every output that reads it -- the s time steps i = j0*s - s/2 .. j0*s + s/2 - 1 -- for all mel bins (or one
+// mel half when SPLIT).  Outputs are enumerated as 8-mel chunks in memory order, so the warp's stores are contiguous
+// 16-byte (bf16) / 32-byte (fp32) pieces: each input is read once from global memory, each output written once.
+template <typename TOut, bool SPLIT>
+__global__ void upsample_warp_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias_p,
+                                     TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
+  extern __shared__ float sm[];
+  float* sw = sm;                                   // [2s*3]
+  const int wpb = blockDim.x >> 5;
+  const int rowlen = mels + 2;
+  float* sin = sm + 2 * s * 3 + (threadIdx.x >> 5) * 2 * rowlen;   // per warp: rows j0-1 and j0, with a zero halo column each side
   for (int i = threadIdx.x; i < 2 * s * 3; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const int To = Tm * s, half = mels / 2, g_per_t = mels / 8;
-  const int64_t n = (int64_t)B * To * g_per_t;
+  const int lane = threadIdx.x & 31;
+  const int To = Tm * s, half = mels / 2;
+  const int planes = SPLIT ? 2 : 1;
+  const int gpr = (SPLIT ? half : mels) / 8;        // 8-mel chunks per output row (of one plane)
   const float bias = __ldg(bias_p);
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int gi = (int)(idx % g_per_t);
-    const int64_t bt = idx / g_per_t;
-    const int i = (int)(bt % To), b = (int)(bt / To);
-    const int m0 = gi * 8;
-    const int q = i + s / 2, r = q % s, j0 = q / s;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int jj = j0 - a, kh = r + a * s;
-      if (jj < 0 || jj >= Tm) continue;
-      const float* row = in + ((int64_t)b * Tm + jj) * mels;
-      float xv[10];
-#pragma unroll
-      for (int u = 0; u < 10; ++u) {
-        const int mm = m0 - 1 + u;
-        xv[u] = (mm >= 0 && mm < mels) ? __ldg(row + mm) : 0.f;
-      }
-      const float w0 = sw[kh * 3 + 0], w1 = sw[kh * 3 + 1], w2 = sw[kh * 3 + 2];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)  // out[m] += in[m+1] w[.,0] + in[m] w[.,1] + in[m-1] w[.,2]
-        acc[j] = fmaf(xv[j + 2], w0, fmaf(xv[j + 1], w1, fmaf(xv[j], w2, acc[j])));
+  const int64_t ntask = (int64_t)B * (Tm + 1);
+  for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < ntask; task += (int64_t)gridDim.x * wpb) {
+    const int b = (int)(task / (Tm + 1)), j0 = (int)(task - (int64_t)b * (Tm + 1));
+    __syncwarp();
+    for (int i = lane; i < 2 * rowlen; i += 32) {
+      const int rr = i / rowlen, mm = i - rr * rowlen - 1;   // rr = 0 -> frame j0-1, 1 -> frame j0
+      const int j = j0 - 1 + rr;
+      sin[i] = (j >= 0 && j < Tm && mm >= 0 && mm < mels) ? __ldg(in + ((int64_t)b * Tm + j) * mels + mm) : 0.f;
     }
+    __syncwarp();
+    for (int pl = 0; pl < planes; ++pl) {
+      for (int k = lane; k < s * gpr; k += 32) {
+        const int r = k / gpr, gi = k - r * gpr;
+        const int i = j0 * s + r - s / 2;            // output time step; its taps are kh = r (frame j0) and r + s (frame j0-1)
+        if (i < 0 || i >= To) continue;
+        const int m0 = pl * half * (SPLIT ? 1 : 0) + gi * 8;
+        const float* x1 = sin + rowlen + m0;        // frame j0, element m0-1 at x1[0]
+        const float* x0 = sin + m0;                 // frame j0-1
+        const float a0 = sw[r * 3], a1 = sw[r * 3 + 1], a2 = sw[r * 3 + 2];
+        const float c0 = sw[(r + s) * 3], c1 = sw[(r + s) * 3 + 1], c2 = sw[(r + s) * 3 + 2];
+        float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.4f * acc[j]);
-    TOut* dst = (m0 < half) ? out0 + bt * half + m0 : out1 + bt * half + (m0 - half);
-    if (sizeof(TOut) == 2) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                                  *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-    } else {
-      reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        for (int j = 0; j < 8; ++j) {  // out[m] = sum_kw in[m + 1 - kw] * w[kh][kw]
+          float v = bias;
+          v = fmaf(x1[j + 2], a0, fmaf(x1[j + 1], a1, fmaf(x1[j], a2, v)));
+          v = fmaf(x0[j + 2], c0, fmaf(x0[j + 1], c1, fmaf(x0[j], c2, v)));
+          acc[j] = fmaxf(v, 0.4f * v);
+        }
+        const int64_t bt = (int64_t)b * To + i;
+        TOut* dst = SPLIT ? (pl == 0 ? out0 : out1) + bt * half + gi * 8 : out0 + bt * mels + gi * 8;
+        if (sizeof(TOut) == 2) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                      *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+        } else {
+          reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
     }
   }
 }
@@ -413,8 +534,13 @@ int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* o
   if (n == 0) return 0;
   int grid = ew_grid(n, 256);
   size_t smem = 2 * (size_t)s * 3 * sizeof(float);
-  if (split && (mels / 2) % 8 == 0) {
-    upsample_split8_kernel<TOut><<<ew_grid(n / 8, 256), 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+  if (mels % 16 == 0 && (reinterpret_cast<uintptr_t>(out0) % 16) == 0 && (!split || reinterpret_cast<uintptr_t>(out1) % 16 == 0)) {
+    const int wpb = 8;
+    const size_t sm2 = smem + (size_t)wpb * 2 * (mels + 2) * sizeof(float);
+    const int64_t ntask = (int64_t)B * (Tm + 1);
+    const int g2 = (int)std::min<int64_t>(cdiv(ntask, wpb), (int64_t)num_sms() * 16);
+    if (split) upsample_warp_kernel<TOut, true><<<g2, wpb * 32, sm2, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    else upsample_warp_kernel<TOut, false><<<g2, wpb * 32, sm2, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
     FWN_LAUNCH_CHECK();
     return 0;
   }
