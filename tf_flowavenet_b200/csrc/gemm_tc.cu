@@ -27,7 +27,7 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane group)
+constexpr int NUM_THREADS = 320;      // default CTA size (warp 0 TMA, warp 1 MMA, 8 epilogue warps); the gate kernel uses 576, see Cfg::THREADS
 constexpr int EPI_THREADS = 256;
 constexpr int MAX_SEG = 4;
 
@@ -243,7 +243,7 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
 // (TMA fill + operand read drop from 192 to 128 bytes per cycle per SM).
 template <int EPI, int BN, bool WS, bool PAIR = false>
 struct Cfg {
-  static constexpr bool STAGED = (EPI == EPI_GATE) || (EPI == EPI_RES_SKIP) || (EPI == EPI_PLAIN && BN >= 128);
+  static constexpr bool STAGED = (EPI == EPI_GATE) || (EPI == EPI_RES_SKIP) || (EPI == EPI_PLAIN && BN == 128);
   static constexpr bool IN_PLACE = (EPI == EPI_RES_SKIP);                 // staging tile is TMA-loaded, updated in place, TMA-stored
   static constexpr int OUT_COLS = (EPI == EPI_GATE) ? BN / 2 : BN;        // bf16 output columns per tile
   static constexpr int SUBTILES = STAGED ? OUT_COLS / 64 : 0;             // [128 rows x 64 cols] 16 KB boxes
@@ -252,15 +252,19 @@ struct Cfg {
   // so a buffer is refilled a full tile after the group that stored from it moved on (lazy release, nobody waits on a
   // store it just issued)
   static constexpr int NSTG = STAGED ? (IN_PLACE ? 3 : 2) : 0;
-  // epilogue organisation: 2 = two groups of four warps alternate tiles (short, latency-bound tiles);
-  //                        1 = all eight warps share every tile, splitting its columns (long MMA-bound gate tiles)
-  static constexpr int GROUPS = (EPI == EPI_GATE) ? 1 : 2;
-  static constexpr int BIAS_BYTES = WS ? BN * 4 : 0;   // weight-stationary CTAs keep their column tile's bias in smem
+  // epilogue organisation: GROUPS groups of WPG warps; the groups alternate tiles (each owns one TMEM stage and one staging
+  // buffer) so the latency chains of consecutive tiles overlap; with WPG == 8 the two warps of a TMEM lane group split the
+  // tile's columns.  The MUFU-heavy gate epilogue is issue-latency-bound and gets 16 warps, the others 8.
+  static constexpr int GROUPS = 2;
+  static constexpr int WPG = (EPI == EPI_GATE) ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * GROUPS * WPG;
+  static constexpr int LDW_MAX = (EPI == EPI_GATE) ? 32 : 64;   // accumulator columns fetched per tcgen05.wait::ld
+  static constexpr int BIAS_BYTES = WS ? BN * 4 : 2048;   // bias in smem: the CTA's own column tile (WS) or all <= 512 columns
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // per-CTA share of the weight box
   static constexpr int WS_CHUNKS = 4;
   static constexpr int W_BYTES = WS ? WS_CHUNKS * B_BYTES : 0;
   static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int BUDGET = 225 * 1024 - NSTG * STG_BYTES - W_BYTES;
+  static constexpr int BUDGET = 223 * 1024 - NSTG * STG_BYTES - W_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + BIAS_BYTES + 256;
@@ -282,26 +286,26 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
   const EpiArgs& e = a.e;
   const int col = n_tile * BN + c0;  // global column of v[0]
   float acc[16];
-  if (WS) {  // this CTA's column tile never changes: bias staged once in shared memory (broadcast 128-bit reads)
+  {  // bias from shared memory (broadcast 128-bit reads): WS kernels stage their own column tile, the others all columns
+    const float* bp = sbias + (WS ? c0 : col);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+      const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * j);
       acc[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
       acc[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
       acc[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
       acc[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + ((col + j < a.N) ? __ldg(e.bias + col + j) : 0.f);
   }
   if (EPI == EPI_GATE) {
     // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124); 16 columns -> 8 channels = one 16-byte chunk
     uint32_t p[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float o0 = tanh_fast(acc[4 * j]) * sigmoid_fast(acc[4 * j + 1]);
-      float o1 = tanh_fast(acc[4 * j + 2]) * sigmoid_fast(acc[4 * j + 3]);
+      // tanh(f) * sigmoid(g) = t + t*tanh(g/2) with t = tanh(f)/2 : 2 MUFU + 3 FP32 ops per output
+      const float t0 = 0.5f * tanh_fast(acc[4 * j]), t1 = 0.5f * tanh_fast(acc[4 * j + 2]);
+      const float o0 = fmaf(tanh_fast(0.5f * acc[4 * j + 1]), t0, t0);
+      const float o1 = fmaf(tanh_fast(0.5f * acc[4 * j + 3]), t1, t1);
       p[j] = pack_bf16(o0, o1);
     }
     *reinterpret_cast<uint4*>(stg + stg_off(r, c0 / 2)) = make_uint4(p[0], p[1], p[2], p[3]);
@@ -387,7 +391,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
 
 // ---------------------------------------------------------------- the kernel
 template <int EPI, int BN, bool WS, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_kernel(const __grid_constant__ TcArgs a) {
   using C = Cfg<EPI, BN, WS, PAIR>;
   static_assert(!(WS && PAIR), "the CTA-pair variant is for the streaming kernel");
   extern __shared__ uint8_t smem_raw[];
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, (C::GROUPS == 2 ? 4 : 8) * (PAIR ? 2 : 1));   // one arrive per warp draining this stage
+      mbar_init(tmem_empty + i, C::WPG * (PAIR ? 2 : 1));   // one arrive per warp draining this stage
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(in_full + i, 1);
@@ -451,11 +455,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (WS) {
-    for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {
-      const int col = ws_n * BN + i;
-      sbias[i] = col < a.N ? __ldg(a.e.bias + col) : 0.f;
-    }
+  for (int i = threadIdx.x; i < C::BIAS_BYTES / 4; i += C::THREADS) {
+    const int col = (WS ? ws_n * BN : 0) + i;
+    sbias[i] = col < a.N ? __ldg(a.e.bias + col) : 0.f;
   }
   if (warp == 1) {
     if (PAIR) tmem_alloc_2sm<C::TMEM_COLS>(tmem_ptr);
@@ -575,9 +577,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   } else {
     // ===================== epilogue (warps 2..9): two groups of four warps alternate tiles =====================
     const int lg = warp & 3;            // TMEM lane group this warp may access
-    const int grp = C::GROUPS == 2 ? (warp - 2) >> 2 : 0;    // GROUPS==2: group g drains TMEM stage g (tiles it % 2 == g)
-    const int half = C::GROUPS == 1 ? (warp - 2) >> 2 : 0;   // GROUPS==1: which half of every tile's columns this warp owns
-    constexpr int CWID = C::GROUPS == 1 ? BN / 2 : BN;       // accumulator columns per warp
+    const int grp = (warp - 2) / C::WPG;                     // group g drains TMEM stage g (tiles it % 2 == g)
+    const int half = C::WPG == 8 ? ((warp - 2) % 8) >> 2 : 0;   // WPG==8: which half of the tile's columns this warp owns
+    constexpr int CWID = C::WPG == 8 ? BN / 2 : BN;          // accumulator columns per warp
     const int cbeg = half * CWID;
     const int r = lg * 32 + lane;
     double ls_sum = 0.0;
@@ -596,8 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       if (C::STAGED) {
         // the store this warp issued from this staging slice (tile it-2) has had a whole tile to read it
         if (lane == 0) {
-          if (C::GROUPS == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           if (C::IN_PLACE && it >= 2) mbar_arrive(in_empty + ((it - 2) % 3));   // lazy release -> input of tile it+1 may land there
         }
         __syncwarp();
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       mbar_wait(tmem_full + as, aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN);
-      constexpr int LDW = CWID >= 64 ? 64 : CWID;   // accumulator columns fetched per tcgen05.wait::ld
+      constexpr int LDW = CWID >= C::LDW_MAX ? C::LDW_MAX : CWID;
 #pragma unroll
       for (int cc = cbeg; cc < cbeg + CWID; cc += LDW) {
         uint32_t v[LDW];
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             om = (a.e.has_res && n_tile * BN < a.e.F) ? 0 : 1;
             ocol = (n_tile * BN) % a.e.F;
           }
-          constexpr int SPW = C::SUBTILES / (C::GROUPS == 1 ? 2 : 1);   // 64-column sub-tiles per warp
+          constexpr int SPW = C::SUBTILES / (C::WPG == 8 ? 2 : 1);   // 64-column sub-tiles per warp
 #pragma unroll
           for (int jj = 0; jj < SPW; ++jj) {
             const int j = half * SPW + jj;
@@ -744,7 +745,7 @@ static int launch(const TcArgs& a, cudaStream_t st) {
   if (PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -756,7 +757,7 @@ static int launch(const TcArgs& a, cudaStream_t st) {
     cfg.numAttrs = 1;
     FWN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, WS, PAIR>, a));
   } else {
-    tc_gemm_kernel<EPI, BN, WS, PAIR><<<grid, NUM_THREADS, C::SMEM, st>>>(a);
+    tc_gemm_kernel<EPI, BN, WS, PAIR><<<grid, C::THREADS, C::SMEM, st>>>(a);
   }
   FWN_LAUNCH_CHECK();
   return 0;
@@ -959,7 +960,7 @@ int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, i
   if (tc::make_w_map(&a.mapB, w, Npad, Kpad, std::min(bn, Npad))) return 1;
   a.B = B; a.Ti = T; a.tiles_per_utt = (T + tc::BM - 1) / tc::BM; a.N = Cout; a.n_tiles = (Cout + bn - 1) / bn;
   a.e.bias = bias; a.e.out0 = y; a.e.ld = Cout; a.e.relu = relu; a.e.F = Cout;
-  if (bn >= 128 && tc::make_store_map(&a.mapOut[0], y, B, T, Cout, Cout)) return 1;  // staged TMA-store epilogue
+  if (bn == 128 && tc::make_store_map(&a.mapOut[0], y, B, T, Cout, Cout)) return 1;  // staged TMA-store epilogue
   return tc::tc_launch(a, EPI_PLAIN, bn, false, st);
 }
 
