@@ -150,3 +150,35 @@ def test_host_entry_points_and_chunked_synthesis():
     # the Python wrapper of the same entry point, as used by FloWaveNet.reverse_sharded
     again = net.reverse_chunk(z[:, :mid + halo].contiguous().cuda(), c[:, :(mid + halo) // 4].contiguous().cuda(), 0, halo)
     assert torch.equal(again, outs[0])
+
+
+def test_synthesis_caller_npy_to_wav(tmp_path):
+    """synthesize.py:23-49 counterpart: .npy mels in, wav files out; the wav equals the device path's waveform (16-bit PCM)."""
+    import types
+    import tf_flowavenet_b200 as P
+    from tf_flowavenet_b200 import synthesize as S
+    hp = O.HP(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=(2, 2))
+    params = O.synthetic_params(hp, 9)
+    hparams = P.HParams(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=[2, 2], sample_rate=8000, temp=0.7)
+    mels, out = tmp_path / "mels", tmp_path / "out"
+    mels.mkdir()
+    rng = np.random.default_rng(1)
+    for i, frames in enumerate((16, 23)):  # ragged lengths
+        np.save(mels / ("utt%d.npy" % i), rng.uniform(0, 1, (frames, 8)).astype(np.float32))
+    np.savez(tmp_path / "w.npz", **{k: v.numpy() for k, v in params.items()})
+    names = S.synthesize(types.SimpleNamespace(weights=str(tmp_path / "w.npz"), mels_dir=str(mels), output_dir=str(out), seed=5), hparams)
+    assert names == ["utt0.npy", "utt1.npy"]
+    # reproduce utterance 0 through the device API with the same z stream
+    model = S.get_model(hparams, {k: v.numpy() for k, v in params.items()})
+    r2 = np.random.default_rng(5)
+    mel0 = np.load(mels / "utt0.npy")
+    z0 = (r2.standard_normal((1, 16 * 4, 1)) * 0.7).astype(np.float32)
+    want = model.reverse(torch.from_numpy(z0).cuda(), torch.from_numpy(mel0[None]).cuda()).cpu().numpy().reshape(-1)
+    got, sr = S.read_wav(str(out / "utt0.wav"))
+    assert sr == 8000 and got.shape == want.shape
+    np.testing.assert_allclose(got, np.clip(want, -1, 1), atol=1.0 / 32767 + 1e-6)
+    got1, _ = S.read_wav(str(out / "utt1.wav"))
+    assert got1.shape == (23 * 4,)
+    # and against the oracle on the same z (fp32 tolerance of BASELINE: 1e-3 max-abs)
+    ref = O.reverse(params, hp, torch.from_numpy(z0), torch.from_numpy(mel0[None]), torch.float64).numpy().reshape(-1)
+    assert np.abs(want - ref).max() < 1e-3
