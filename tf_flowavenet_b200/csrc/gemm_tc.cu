@@ -188,6 +188,75 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Issue the (up to four) K=16 MMAs of one 64-wide K chunk and commit them to `bar`, from ONE convergent asm block predicated
+// by elect.sync.  Issuing each tcgen05.mma from inside a divergent `if (lane == 0)` makes ptxas wrap every UTCHMMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~100 dependent instructions per chunk on one warp, which was slower than the
+// 512 cycles of tensor work it feeds.  Descriptors advance by 32 bytes (+2 in 16-byte units) per K step inside the swizzle atom.
+template <bool PAIR>
+__device__ __forceinline__ void umma_chunk_commit(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                                  uint32_t ksteps, uint32_t bar) {
+  if (PAIR) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pacc, pt, p1, p2, p3;\n"
+        ".reg .b64 da, db;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pacc, %4, 0;\n"
+        "setp.eq.u32 pt, 0, 0;\n"
+        "setp.gt.u32 p1, %5, 1;\n and.pred p1, p1, pe;\n"
+        "setp.gt.u32 p2, %5, 2;\n and.pred p2, p2, pe;\n"
+        "setp.gt.u32 p3, %5, 3;\n and.pred p3, p3, pe;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pacc;\n"
+        "add.u64 da, %1, 2;\n add.u64 db, %2, 2;\n"
+        "@p1 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n"
+        "add.u64 da, %1, 4;\n add.u64 db, %2, 4;\n"
+        "@p2 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n"
+        "add.u64 da, %1, 6;\n add.u64 db, %2, 6;\n"
+        "@p3 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %7;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(ksteps), "r"(bar), "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pacc, pt, p1, p2, p3;\n"
+        ".reg .b64 da, db;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pacc, %4, 0;\n"
+        "setp.eq.u32 pt, 0, 0;\n"
+        "setp.gt.u32 p1, %5, 1;\n and.pred p1, p1, pe;\n"
+        "setp.gt.u32 p2, %5, 2;\n and.pred p2, p2, pe;\n"
+        "setp.gt.u32 p3, %5, 3;\n and.pred p3, p3, pe;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pacc;\n"
+        "add.u64 da, %1, 2;\n add.u64 db, %2, 2;\n"
+        "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+        "add.u64 da, %1, 4;\n add.u64 db, %2, 4;\n"
+        "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+        "add.u64 da, %1, 6;\n add.u64 db, %2, 6;\n"
+        "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(ksteps), "r"(bar)
+        : "memory");
+  }
+}
+// commit only (accumulator-complete signal), convergent + elect-predicated
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  if (PAIR) {
+    asm volatile(
+        "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -534,6 +603,8 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
     int m_tile, n_tile;
+    const uint32_t stage0 = smem_u32(stage_base), w0 = smem_u32(w_base);
+    const uint64_t desc_hi = make_smem_desc(0);   // everything but the start-address field
     if (WS) {
       mbar_wait(w_full, 0);
       tcgen05_fence_after();
@@ -545,33 +616,22 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
       uint32_t accumulate = 0;
       int c = 0;
       for (int s = 0; s < a.nseg; ++s) {
-        for (int ch = 0; ch < a.nchunk[s]; ++ch, ++c) {
+        const int nch = a.nchunk[s];
+        const uint32_t last_ks = (uint32_t)a.last_ksteps[s];
+        for (int ch = 0; ch < nch; ++ch, ++c) {
           mbar_wait(full_bar + stage, phase);
           tcgen05_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
-            const uint32_t sb = WS ? smem_u32(w_base + (size_t)c * C::B_BYTES) : sa + A_BYTES;
-            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
-            const int ksteps = (ch == a.nchunk[s] - 1) ? a.last_ksteps[s] : BK / UMMA_K;
-            for (int k = 0; k < ksteps; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte address units
-              if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-              else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-              accumulate = 1;
-            }
-            if (PAIR) umma_commit_2sm(empty_bar + stage);  // release the stage in both CTAs
-            else umma_commit(empty_bar + stage);           // frees the smem stage once these MMAs have read it
-          }
+          const uint32_t sa = stage0 + (uint32_t)stage * C::STAGE_BYTES;
+          const uint32_t sb = WS ? w0 + (uint32_t)c * C::B_BYTES : sa + A_BYTES;
+          const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF), bdesc = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
+          const uint32_t ksteps = (ch == nch - 1) ? last_ks : (uint32_t)(BK / UMMA_K);
+          // all 32 lanes stay convergent; one elected lane issues the chunk's MMAs and the commit that frees the stage
+          umma_chunk_commit<PAIR>(tmem_d, adesc, bdesc, idesc, accumulate, ksteps, smem_u32(empty_bar + stage));
           accumulate = 1;
-          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (lane == 0) {                             // accumulator complete -> epilogue (of both CTAs for a pair)
-        if (PAIR) umma_commit_2sm(tmem_full + as);
-        else umma_commit(tmem_full + as);
-      }
-      __syncwarp();
+      umma_commit_elect<PAIR>(smem_u32(tmem_full + as));   // accumulator complete -> epilogue (of both CTAs for a pair)
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
