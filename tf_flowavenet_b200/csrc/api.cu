@@ -177,6 +177,7 @@ static int host_buffers(Model* m, int B, int T, float** d_x, float** d_c, float*
     FWN_CUDA(cudaMalloc(&m->host_io, need));
     m->host_io_bytes = need;
   }
+  if (!m->host_stream) FWN_CUDA(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
   float* p = (float*)m->host_io;
   *d_x = p;
   *d_out = p + nx;
@@ -191,7 +192,7 @@ int fwn_forward_host(fwn_handle h, const float* x, const float* c, const int32_t
   Model* m = h->m;
   float *d_x, *d_c, *d_out, *d_s;
   if (host_buffers(m, B, T, &d_x, &d_c, &d_out, &d_s)) return 1;
-  cudaStream_t st = 0;
+  cudaStream_t st = m->host_stream;
   FWN_CUDA(cudaMemcpyAsync(d_x, x, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
   FWN_CUDA(cudaMemcpyAsync(d_c, c, (size_t)B * (T / m->hop) * m->cfg.num_mels * 4, cudaMemcpyHostToDevice, st));
   m->launches = 0;
@@ -211,7 +212,7 @@ int fwn_reverse_host(fwn_handle h, const float* z, const float* c, const int32_t
   Model* m = h->m;
   float *d_x, *d_c, *d_out, *d_s;
   if (host_buffers(m, B, T, &d_x, &d_c, &d_out, &d_s)) return 1;
-  cudaStream_t st = 0;
+  cudaStream_t st = m->host_stream;
   FWN_CUDA(cudaMemcpyAsync(d_x, z, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
   FWN_CUDA(cudaMemcpyAsync(d_c, c, (size_t)B * (T / m->hop) * m->cfg.num_mels * 4, cudaMemcpyHostToDevice, st));
   m->launches = 0;

@@ -12,6 +12,7 @@
 // No squeeze, unsqueeze, split, concat or change_order kernel ever runs on the model path.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -134,13 +135,21 @@ int model_create(const fwn_config* cfg, Model** out) {
   return 0;
 }
 
+void model_drop_graphs(Model* m) {
+  for (auto& g : m->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
+}
+
 void model_destroy(Model* m) {
   if (!m) return;
+  model_drop_graphs(m);
   for (auto e : m->prof_ev) cudaEventDestroy(e);
   cudaFree(m->raw);
   cudaFree(m->pack);
   cudaFree(m->host_ws);
   cudaFree(m->host_io);
+  if (m->host_stream) cudaStreamDestroy(m->host_stream);
   delete m;
 }
 
@@ -461,6 +470,7 @@ int model_prepack(Model* m, cudaStream_t st) {
       fp.rs_b[n] = reinterpret_cast<float*>(base + fo.rs_b[n]);
     }
   }
+  model_drop_graphs(m);
   m->packed = true;
   m->plan_B = m->plan_T = -1;  // tensor maps (tcgen05 engine) must be rebuilt
   return 0;
@@ -729,6 +739,80 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   return 0;
 }
 
+// The dependent chain of flows of one pass, on the workspace's X buffer (all pointers inside are workspace / pack pointers,
+// so the captured graph stays valid as long as the workspace and the prepacked weights do).
+static int run_chain(Model* m, const Workspace& w, int B, int T, bool reverse, cudaStream_t st) {
+  const fwn_config& cf = m->cfg;
+  if (!reverse) {
+    for (int i = 0; i < cf.n_block; ++i)
+      for (int j = 0; j < cf.n_flow; ++j)
+        if (run_flow(m, w, m->flows[(size_t)i * cf.n_flow + j], w.x, B, T >> (i + 1), false, st)) return 1;
+  } else {
+    for (int i = cf.n_block - 1; i >= 0; --i)
+      for (int j = cf.n_flow - 1; j >= 0; --j)
+        if (run_flow(m, w, m->flows[(size_t)i * cf.n_flow + j], w.x, B, T >> (i + 1), true, st)) return 1;
+  }
+  return 0;
+}
+
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_GRAPH");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// First call for a (direction, shape, workspace): run eagerly (also sets kernel attributes, builds tensor maps).
+// Second call: capture the chain into a graph and launch it.  Later calls: replay.
+static int run_chain_graphed(Model* m, const Workspace& w, int B, int T, bool reverse, cudaStream_t st) {
+  if (!graphs_enabled() || m->prof_on) return run_chain(m, w, B, T, reverse, st);
+  Model::PassGraph* g = nullptr;
+  for (auto& e : m->graphs)
+    if (e.reverse == (int)reverse && e.B == B && e.T == T && e.ws == (const void*)w.sums) g = &e;
+  if (!g) {
+    if (m->graphs.size() >= 16) model_drop_graphs(m);
+    m->graphs.push_back(Model::PassGraph{(int)reverse, B, T, (const void*)w.sums, 0, nullptr, 0});
+    return run_chain(m, w, B, T, reverse, st);
+  }
+  if (g->state == 0) {
+    const int64_t before = m->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();  // e.g. the legacy default stream cannot be captured: stay eager on this stream/shape
+      g->state = -1;
+      return run_chain(m, w, B, T, reverse, st);
+    }
+    const int rc = run_chain(m, w, B, T, reverse, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g->state = -1;  // capture not possible: stay eager for this shape
+      if (rc) return 1;
+      return run_chain(m, w, B, T, reverse, st);
+    }
+    g->launches = m->launches - before;
+    m->launches = before;
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      g->exec = nullptr;
+      g->state = -1;
+      return run_chain(m, w, B, T, reverse, st);
+    }
+    g->state = 1;
+  }
+  if (g->state == 1) {
+    FWN_CUDA(cudaGraphLaunch(g->exec, st));
+    m->launches += g->launches;
+    return 0;
+  }
+  return run_chain(m, w, B, T, reverse, st);
+}
+
 static int check_pass_args(Model* m, const void* x, const void* c, const int32_t* g, int B, int T, void* ws, int64_t ws_bytes,
                            Workspace* w) {
   FWN_CHECK(m && m->packed, "model not prepacked: call fwn_prepack after fwn_set_param");
@@ -745,25 +829,31 @@ int model_forward(Model* m, const float* x, const float* c, const int32_t* g, in
   Workspace w;
   if (check_pass_args(m, x, c, g, B, T, ws, ws_bytes, &w)) return 1;
   if (prepare_engine(m, w, B, T, st)) return 1;
-  float* X = z_out ? z_out : w.x;
-  if (X != x) FWN_CUDA(cudaMemcpyAsync(X, x, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
+  // the flow variable lives in the workspace for the whole pass (fixed address -> the flow chain can be a CUDA graph)
+  float* X = w.x;
+  FWN_CUDA(cudaMemcpyAsync(X, x, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
   FWN_CUDA(cudaMemsetAsync(w.sums, 0, 8 * sizeof(double), st));
   if (ddi) FWN_CUDA(cudaMemsetAsync(m->d_an_logdet, 0, sizeof(double), st));
   if (run_upsample(m, w, c, B, T, st)) return 1;
   // The speaker embedding g is looked up, tiled and squeezed by the reference (model.py:330-336) but never
   // reaches a kernel: WaveNet.__call__ drops it (modules.py:188-189).  Outputs do not depend on g.
   const fwn_config& cf = m->cfg;
-  for (int i = 0; i < cf.n_block; ++i) {
-    const int Ti = T >> (i + 1);
-    for (int j = 0; j < cf.n_flow; ++j) {
-      const FlowPack& fp = m->flows[(size_t)i * cf.n_flow + j];
-      if (ddi && ddi_flow(m, fp, X, (int64_t)B * Ti, w.ddi, st)) return 1;
-      if (run_flow(m, w, fp, X, B, Ti, false, st)) return 1;
+  if (ddi) {
+    for (int i = 0; i < cf.n_block; ++i) {
+      const int Ti = T >> (i + 1);
+      for (int j = 0; j < cf.n_flow; ++j) {
+        const FlowPack& fp = m->flows[(size_t)i * cf.n_flow + j];
+        if (ddi_flow(m, fp, X, (int64_t)B * Ti, w.ddi, st)) return 1;
+        if (run_flow(m, w, fp, X, B, Ti, false, st)) return 1;
+      }
     }
+  } else if (run_chain_graphed(m, w, B, T, false, st)) {
+    return 1;
   }
   if (sumsq(X, w.sums + 1, (int64_t)B * T, st)) return 1;
   finish_forward_kernel<<<1, 1, 0, st>>>(w.sums, m->d_an_logdet, logp_out, logdet_out, (double)B * T);
   FWN_LAUNCH_CHECK();
+  if (z_out) FWN_CUDA(cudaMemcpyAsync(z_out, X, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -775,15 +865,11 @@ int model_reverse(Model* m, const float* z, const float* c, const int32_t* g, in
   FWN_CHECK(m->rev_ok, "fused reverse needs an even n_flow: with odd n_flow the reference's reverse is not the inverse of forward "
                        "(change_order parity, model.py:199,359) -- use the per-op Block/Flow API for that case");
   if (prepare_engine(m, w, B, T, st)) return 1;
-  float* X = x_out;
-  if (X != z) FWN_CUDA(cudaMemcpyAsync(X, z, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
+  float* X = w.x;
+  FWN_CUDA(cudaMemcpyAsync(X, z, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
   if (run_upsample(m, w, c, B, T, st)) return 1;
-  const fwn_config& cf = m->cfg;
-  for (int i = cf.n_block - 1; i >= 0; --i) {
-    const int Ti = T >> (i + 1);
-    for (int j = cf.n_flow - 1; j >= 0; --j)
-      if (run_flow(m, w, m->flows[(size_t)i * cf.n_flow + j], X, B, Ti, true, st)) return 1;
-  }
+  if (run_chain_graphed(m, w, B, T, true, st)) return 1;
+  if (x_out != X) FWN_CUDA(cudaMemcpyAsync(x_out, X, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -75,7 +75,12 @@ struct Model {
   int64_t host_ws_bytes = 0;
   void* host_io = nullptr;
   int64_t host_io_bytes = 0;
+  cudaStream_t host_stream = nullptr;  // non-blocking stream of the *_host entry points (capturable, unlike stream 0)
   int64_t launches = 0;  // kernels launched by the last pass (bench.py's gpu_launches)
+  // CUDA graphs of the per-pass flow chain, keyed by (direction, B, T, workspace): the chain is ~200-400 dependent
+  // launches, so replaying one graph removes the per-launch gaps (decisive for short utterances)
+  struct PassGraph { int reverse, B, T; const void* ws; int state; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<PassGraph> graphs;
   // optional per-kernel-family CUDA-event timing (fwn_profile_*): bench.py's roofline numbers
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -98,6 +103,7 @@ int model_forward(Model* m, const float* x, const float* c, const int32_t* g, in
 int model_reverse(Model* m, const float* z, const float* c, const int32_t* g, int B, int T, float* x_out, void* ws, int64_t ws_bytes,
                   cudaStream_t st);
 int model_receptive_halo(const Model* m);
+void model_drop_graphs(Model* m);
 
 // engine dispatch (engine.cu): fp32 -> CUDA-core implicit GEMM, mixed -> tcgen05
 int prepare_engine(Model* m, const Workspace& w, int B, int T, cudaStream_t st);
