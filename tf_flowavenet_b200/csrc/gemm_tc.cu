@@ -435,9 +435,10 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
     // (2q, 2q+1) = (log_s, t) of transformed element q; ActNorm + coupling in place on the fp32 flow variable
     if (!row_ok) return;
     float* xr = e.X + row * e.Cx;
+    const int q0 = col / 2;
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-      const int q = col / 2 + p;
+      const int q = q0 + p;
       if (q >= e.nq) break;
       const float log_s = acc[2 * p], tt = acc[2 * p + 1];
       const int oa = __ldg(e.a_off + q), ob = __ldg(e.b_off + q);
@@ -455,6 +456,38 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
       xr[oa] = xa;
       xr[ob] = xb;
     }
+  }
+}
+
+// AFFINE fast path on registers: 16 accumulator columns = 8 adjacent (pass-through, transformed) pairs = 16 consecutive floats
+// of the thread's x row, already loaded into x4[0..3]; ActNorm + coupling applied in place in registers.
+__device__ __forceinline__ void affine16_regs(const EpiArgs& e, const float* sbias, int col, const uint32_t* v, float4* x4, bool row_ok,
+                                              double& ls_sum) {
+  const float4* bp = reinterpret_cast<const float4*>(e.an_b + col);
+  const float4* sp = reinterpret_cast<const float4*>(e.an_s + col);
+  const int bo = e.b_odd;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 b4 = __ldg(bp + k), s4 = __ldg(sp + k);
+    const float4 bias4 = *reinterpret_cast<const float4*>(sbias + col + 4 * k);
+    float x[4] = {x4[k].x, x4[k].y, x4[k].z, x4[k].w};
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float ac[4] = {__uint_as_float(v[4 * k]) + bias4.x, __uint_as_float(v[4 * k + 1]) + bias4.y,
+                         __uint_as_float(v[4 * k + 2]) + bias4.z, __uint_as_float(v[4 * k + 3]) + bias4.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float log_s = ac[2 * h], tt = ac[2 * h + 1];
+      const int ib = 2 * h + bo, ia = 2 * h + 1 - bo;
+      if (!e.reverse) {
+        x[ia] = (x[ia] + bb[ia]) * ss[ia];
+        x[ib] = ((x[ib] + bb[ib]) * ss[ib] - tt) * __expf(-log_s);
+        if (row_ok) ls_sum += (double)log_s;   // rows past the utterance end see bias-only accumulators: not part of the log-det
+      } else {
+        x[ib] = (x[ib] * __expf(log_s) + tt) * ss[ib] - bb[ib];
+        x[ia] = x[ia] * ss[ia] - bb[ia];
+      }
+    }
+    x4[k] = make_float4(x[0], x[1], x[2], x[3]);
   }
 }
 
@@ -674,11 +707,36 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
 #pragma unroll
       for (int cc = cbeg; cc < cbeg + CWID; cc += LDW) {
         uint32_t v[LDW];
+        // AFFINE fast path: this batch's LDW columns are LDW consecutive floats of the thread's x row -> fetch them (independent
+        // 128-bit loads, issued before the TMEM wait), update in registers, store once: one memory round trip per batch
+        const int gcol = n_tile * BN + cc;
+        const bool xfast = (EPI == EPI_AFFINE) && a.e.pairs_adjacent && (gcol + LDW <= a.e.Cx) && LDW >= 16;
+        float4 xv[LDW >= 4 ? LDW / 4 : 1];
+        float4* xp = nullptr;
+        if (EPI == EPI_AFFINE && xfast) {
+          xp = reinterpret_cast<float4*>(a.e.X + row * a.e.Cx + gcol);
+          if (row_ok) {
+#pragma unroll
+            for (int k = 0; k < LDW / 4; ++k) xv[k] = xp[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < LDW / 4; ++k) xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < LDW; j += 16) tmem_ld_x16(taddr + cc + j, v + j);
         tmem_ld_wait();
+        if (EPI == EPI_AFFINE && xfast) {
 #pragma unroll
-        for (int j = 0; j < LDW; j += 16) epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cc + j, v + j, stg, have_in, sbias, ls_sum);
+          for (int j = 0; j < LDW; j += 16) affine16_regs(a.e, sbias, gcol + j, v + j, xv + j / 4, row_ok, ls_sum);
+          if (row_ok) {
+#pragma unroll
+            for (int k = 0; k < LDW / 4; ++k) xp[k] = xv[k];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < LDW; j += 16) epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cc + j, v + j, stg, have_in, sbias, ls_sum);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();

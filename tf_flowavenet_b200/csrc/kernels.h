@@ -56,6 +56,7 @@ struct EpiArgs {
   const float* an_s;       // [Cx] exp(3 logs) (forward) or exp(-3 logs) (reverse)
   double* logdet_acc;      // sum of log_s (forward)
   int reverse;
+  int pairs_adjacent, b_odd;  // fast path: pair p of the zero conv's columns = x offsets (2p, 2p+1)
 };
 
 struct GemmArgs {

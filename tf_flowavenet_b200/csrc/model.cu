@@ -284,8 +284,21 @@ int model_prepack(Model* m, cudaStream_t st) {
       fp.Kc = Kc;
       std::string pre = "Block_" + std::to_string(i) + "/Flow_" + std::to_string(j);
       std::string wpre = pre + "/AffineCoupling/WaveNet";
-      // a / b halves in logical order
-      std::vector<int> a_off(x_off.begin(), x_off.begin() + nq), b_off(x_off.begin() + nq, x_off.end());
+      // a / b halves.  Pair q couples pass-through channel q with transformed channel nq+q; every such pair is physically
+      // adjacent (offsets 2p, 2p+1 in some order), so pairs are enumerated in PHYSICAL order p: the zero conv's column pairs
+      // (and a_off / b_off) follow that order and a thread's consecutive columns touch consecutive bytes of its x row.
+      std::vector<int> qperm(nq);
+      for (int q = 0; q < nq; ++q) qperm[q] = q;
+      std::sort(qperm.begin(), qperm.end(), [&](int u, int v) { return x_off[nq + u] < x_off[nq + v]; });
+      std::vector<int> a_off(nq), b_off(nq);
+      bool adjacent = true;
+      for (int p2 = 0; p2 < nq; ++p2) {
+        a_off[p2] = x_off[qperm[p2]];
+        b_off[p2] = x_off[nq + qperm[p2]];
+        adjacent = adjacent && ((a_off[p2] ^ b_off[p2]) == 1) && ((b_off[p2] >> 1) == p2);
+      }
+      fp.pairs_adjacent = adjacent ? 1 : 0;
+      fp.b_odd = (b_off[0] & 1);
       std::vector<int> off2log(cx);
       for (int l = 0; l < cx; ++l) off2log[x_off[l]] = l;
       fo.a_off = store_ints(b, a_off);
@@ -403,19 +416,20 @@ int model_prepack(Model* m, cudaStream_t st) {
         const float* zs = hp.p(wpre + "/ZeroConv1d/scale");
         const int Nz = 2 * nq;
         std::vector<double> W((size_t)F * Nz, 0.0), B(Nz, 0.0);
-        for (int q = 0; q < nq; ++q) {
+        for (int p2 = 0; p2 < nq; ++p2) {   // column pair p2 <- logical transformed channel q = qperm[p2]
+          const int q = qperm[p2];
           if (c.affine) {
             const double e0 = exp(3.0 * (double)zs[q]), e1 = exp(3.0 * (double)zs[nq + q]);
             for (int k = 0; k < F; ++k) {
-              W[(size_t)k * Nz + 2 * q] = zk[(size_t)k * out_ch + q] * e0;
-              W[(size_t)k * Nz + 2 * q + 1] = zk[(size_t)k * out_ch + nq + q] * e1;
+              W[(size_t)k * Nz + 2 * p2] = zk[(size_t)k * out_ch + q] * e0;
+              W[(size_t)k * Nz + 2 * p2 + 1] = zk[(size_t)k * out_ch + nq + q] * e1;
             }
-            B[2 * q] = zb[q] * e0;
-            B[2 * q + 1] = zb[nq + q] * e1;
+            B[2 * p2] = zb[q] * e0;
+            B[2 * p2 + 1] = zb[nq + q] * e1;
           } else {
             const double e0 = exp(3.0 * (double)zs[q]);
-            for (int k = 0; k < F; ++k) W[(size_t)k * Nz + 2 * q + 1] = -(double)zk[(size_t)k * out_ch + q] * e0;
-            B[2 * q + 1] = -(double)zb[q] * e0;
+            for (int k = 0; k < F; ++k) W[(size_t)k * Nz + 2 * p2 + 1] = -(double)zk[(size_t)k * out_ch + q] * e0;
+            B[2 * p2 + 1] = -(double)zb[q] * e0;
           }
         }
         int ld;
@@ -732,6 +746,8 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     g.e.an_b = fp.an_b; g.e.an_s = reverse ? fp.an_is : fp.an_s;
     g.e.logdet_acc = reverse ? nullptr : w.sums;
     g.e.reverse = reverse;
+    g.e.pairs_adjacent = fp.pairs_adjacent;
+    g.e.b_odd = fp.b_odd;
     prof_begin(m, PROF_ZERO_AFFINE, 2.0 * rows * F * (c.affine ? fp.Cx : fp.nq), st);
     if (run_gemm(m, g, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
     prof_end(m, st);

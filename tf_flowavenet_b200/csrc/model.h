@@ -24,6 +24,7 @@ constexpr int MAX_LAYERS = 8;
 // Prepacked weights of one flow (ActNorm + AffineCoupling/WaveNet), device pointers.
 struct FlowPack {
   int Cx, nq, Kc, cond_half;
+  int pairs_adjacent, b_odd;   // pair p = physical offsets (2p, 2p+1); b_odd: the transformed element is the odd one
   int *a_off, *b_off, *off2log;
   float *an_b, *an_s, *an_is;      // ActNorm bias / exp(3 logs) / exp(-3 logs), physical order
   float *raw_b, *raw_logs;         // the reference-named variables (updated by DDI)
