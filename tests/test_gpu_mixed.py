@@ -78,3 +78,56 @@ def test_mixed_matches_golden_small():
     log_p, logdet, z = net.forward(x, c, return_z=True)
     assert abs(float(log_p) - float(fx["log_p"])) < 1e-2 and abs(float(logdet) - float(fx["logdet"])) < 1e-2
     assert np.abs(z.cpu().numpy() - fx["z"]).max() < 3e-2
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_graph_replay_is_bit_identical_to_eager(dtype):
+    """On a real (capturable) stream the 2nd call captures the flow chain into a CUDA graph and later calls replay it;
+    every call must give bit-identical results, also after the weights change (re-prepack drops the graphs)."""
+    hp, params, fx = load("g1_b2f2l2")
+    from tests.test_gpu_model import make_model
+    net = make_model(hp, params, dtype)
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    z_in = torch.from_numpy(fx["z_in"]).float().cuda()
+    eager_rev = net.reverse(z_in, c)                      # legacy default stream: cannot be captured -> eager
+    eager_fwd = net.forward(x, c, return_z=True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        revs = [net.reverse(z_in, c) for _ in range(4)]   # eager, capture+launch, replay, replay
+        fwds = [net.forward(x, c, return_z=True) for _ in range(4)]
+    side.synchronize()
+    for r in revs:
+        assert torch.equal(r, eager_rev)
+    for f in fwds:
+        assert torch.equal(f[2], eager_fwd[2]) and float(f[0]) == float(eager_fwd[0]) and float(f[1]) == float(eager_fwd[1])
+    # change one ActNorm bias: results must change accordingly (stale graphs would keep the old packed weights)
+    k = "Block_0/Flow_0/ActNorm/b"
+    net.load_variables({k: params[k].numpy() + 0.25})
+    with torch.cuda.stream(side):
+        after = [net.reverse(z_in, c) for _ in range(3)]
+    side.synchronize()
+    assert not torch.equal(after[0], eager_rev)
+    assert torch.equal(after[0], after[1]) and torch.equal(after[1], after[2])
+
+
+@pytest.mark.parametrize("B,frames", [(1, 1), (3, 1), (1, 9), (2, 33)])
+def test_mixed_ragged_and_tiny_shapes(B, frames):
+    """Tiles that are mostly padding (T_i < 128), batch entries that do not fill a tile, T_i not a multiple of 128:
+    TMA zero fill / clipped bulk stores must reproduce the reference's per-utterance zero padding exactly."""
+    import tf_flowavenet_b200 as P
+    from tests.test_gpu_model import make_model
+    hp = O.HP(n_block=3, n_flow=2, n_layer=2, num_mels=16, upsample_scales=(4, 2))   # hop 8 = 2^3
+    params = O.synthetic_params(hp, 55)
+    x, c = O.synthetic_inputs(hp, B, frames * 17, 56, "x")                            # T = 136*frames: ragged vs 128-row tiles
+    net32, net16 = make_model(hp, params, "float32"), make_model(hp, params, "bfloat16")
+    wlp, wld, wz = O.forward(params, hp, x, c, torch.float64)
+    lp32, ld32, z32 = net32.forward(x.cuda(), c.cuda(), return_z=True)
+    lp16, ld16, z16 = net16.forward(x.cuda(), c.cuda(), return_z=True)
+    assert float((z32.cpu().double() - wz).abs().max() / wz.abs().max()) < 1e-4
+    assert float((z16.cpu().double() - wz).abs().max() / wz.abs().max()) < 1e-2
+    assert abs(float(ld32) - float(wld)) < 1e-4 * max(1.0, abs(float(wld))) and abs(float(ld16) - float(wld)) < 1e-2
+    zin, _ = O.synthetic_inputs(hp, B, frames * 17, 57, "z")
+    want = O.reverse(params, hp, zin, c, torch.float64)
+    assert (net32.reverse(zin.cuda(), c.cuda()).cpu().double() - want).abs().max() < 1e-3
+    assert (net16.reverse(zin.cuda(), c.cuda()).cpu().double() - want).abs().max() < 3e-2

@@ -27,8 +27,6 @@ namespace tc {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_THREADS = 320;      // default CTA size (warp 0 TMA, warp 1 MMA, 8 epilogue warps); the gate kernel uses 576, see Cfg::THREADS
-constexpr int EPI_THREADS = 256;
 constexpr int MAX_SEG = 4;
 
 struct alignas(64) TcArgs {
@@ -113,23 +111,6 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
-// D[tmem of both CTAs] (+)= [A0;A1] * [B0;B1]^T : M=256 across the pair, issued by the leader CTA only
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs once all previously issued pair-MMAs have completed
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
 // plain arrive on the barrier at this offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
@@ -173,20 +154,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
 template <int NCOLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Issue the (up to four) K=16 MMAs of one 64-wide K chunk and commit them to `bar`, from ONE convergent asm block predicated
 // by elect.sync.  Issuing each tcgen05.mma from inside a divergent `if (lane == 0)` makes ptxas wrap every UTCHMMA in an
