@@ -131,3 +131,43 @@ def test_mixed_ragged_and_tiny_shapes(B, frames):
     want = O.reverse(params, hp, zin, c, torch.float64)
     assert (net32.reverse(zin.cuda(), c.cuda()).cpu().double() - want).abs().max() < 1e-3
     assert (net16.reverse(zin.cuda(), c.cuda()).cpu().double() - want).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("kw", [dict(n_layer=3), dict(causality=True), dict(affine=False), dict(n_layer=1), dict(n_flow=4, n_block=3)])
+def test_mixed_variants_vs_oracle(kw):
+    """Less-travelled graph variants on the tcgen05 path: 3 layers (skip accumulation over a middle layer, dilation 9),
+    causal padding (taps at t-2d, t-d, t), additive coupling (no log-det term), a single layer, 4 flows x 3 blocks."""
+    from tests.test_gpu_model import make_model
+    base = dict(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=(2, 2))
+    base.update(kw)
+    if base["n_block"] == 3:
+        base["upsample_scales"] = (4, 2)
+    hp = O.HP(**base)
+    params = O.synthetic_params(hp, 91)
+    x, c = O.synthetic_inputs(hp, 2, 40, 92, "x")
+    net = make_model(hp, params, "bfloat16")
+    lp, ld, z = net.forward(x.cuda(), c.cuda(), return_z=True)
+    wlp, wld, wz = O.forward(params, hp, x, c, torch.float64)
+    assert float((z.cpu().double() - wz).abs().max() / wz.abs().max()) < 1e-2
+    assert abs(float(ld) - float(wld)) < 1e-2 and abs(float(lp) - float(wlp)) < 1e-2
+    zin, _ = O.synthetic_inputs(hp, 2, 40, 93, "z")
+    want = O.reverse(params, hp, zin, c, torch.float64)
+    assert (net.reverse(zin.cuda(), c.cuda()).cpu().double() - want).abs().max() < 3e-2
+
+
+def test_mixed_ddi_matches_oracle():
+    """ActNorm data-dependent init (train.py:221,229) through the mixed-precision pass: the statistics are taken on the fp32
+    flow variable, so b / logs agree with the fp32 oracle to bf16-propagation accuracy."""
+    from tests.test_gpu_model import make_model
+    hp = O.HP(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=(2, 2))
+    params = O.synthetic_params(hp, 94)
+    x, c = O.synthetic_inputs(hp, 3, 64, 95, "x")
+    net = make_model(hp, params, "bfloat16")
+    lp, ld = net.initialize_actnorm(x.cuda(), c.cuda())
+    want = O.ddi_init(params, hp, x, c, torch.float64)
+    got = net.variables()
+    for k, v in want.items():
+        if "/ActNorm/" in k:
+            np.testing.assert_allclose(got[k].cpu().numpy(), v.numpy(), rtol=0, atol=2e-2, err_msg=k)
+    wlp, wld, _ = O.forward(want, hp, x, c, torch.float64)
+    assert abs(float(ld) - float(wld)) < 2e-2 and abs(float(lp) - float(wlp)) < 2e-2
