@@ -302,12 +302,22 @@ struct Cfg {
   static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
   static constexpr int BUDGET = 223 * 1024 - NSTG * STG_BYTES - W_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // TMEM accumulator stages: 4 where they fit (BN <= 128) so the MMA warp can run several tiles ahead of the epilogue groups
+  static constexpr int NACC = (BN <= 128) ? 4 : 2;
+  static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + BIAS_BYTES + 256;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // byte offset of the 16-byte chunk holding columns [c, c+8) of row r inside a staged tile (TMA SWIZZLE_128B layout)
 __device__ __forceinline__ uint32_t stg_off(int r, int c) {
   return (uint32_t)((c >> 6) * (BM * 128) + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
@@ -317,7 +327,7 @@ __device__ __forceinline__ uint32_t stg_off(int r, int c) {
 // `stg` = this tile's staging buffer (STAGED kinds); for RES_SKIP it already holds the residual input / running skip sum.
 template <int EPI, int BN, bool WS>
 __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool row_ok, int r, int n_tile, int c0, const uint32_t* v,
-                                           uint8_t* stg, bool have_in, const float* sbias, double& ls_sum) {
+                                           uint8_t* stg, bool have_in, const uint4* inp, const float* sbias, double& ls_sum) {
   using C = Cfg<EPI, BN, WS, false>;
   const EpiArgs& e = a.e;
   const int col = n_tile * BN + c0;  // global column of v[0]
@@ -344,13 +354,12 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
       const float o1 = fmaf(tanh_fast(0.5f * acc[4 * j + 3]), t1, t1);
       p[j] = pack_bf16(o0, o1);
     }
-    *reinterpret_cast<uint4*>(stg + stg_off(r, c0 / 2)) = make_uint4(p[0], p[1], p[2], p[3]);
+    sts128(smem_u32(stg) + stg_off(r, c0 / 2), make_uint4(p[0], p[1], p[2], p[3]));
   } else if (EPI == EPI_RES_SKIP) {
-    uint4* q0 = reinterpret_cast<uint4*>(stg + stg_off(r, c0));
-    uint4* q1 = reinterpret_cast<uint4*>(stg + stg_off(r, c0 + 8));
+    const uint32_t sbase = smem_u32(stg);
     const bool is_res = e.has_res && col < e.F;
-    if (have_in) {
-      const uint4 h0 = *q0, h1 = *q1;
+    if (have_in) {   // residual input / running skip sum: this thread's two 16-byte chunks, pre-loaded from the staging tile
+      const uint4 h0 = inp[0], h1 = inp[1];
       const uint32_t hu[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -373,8 +382,8 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
       }
       p[j] = pack_bf16(lo, hi);
     }
-    *q0 = make_uint4(p[0], p[1], p[2], p[3]);
-    *q1 = make_uint4(p[4], p[5], p[6], p[7]);
+    sts128(sbase + stg_off(r, c0), make_uint4(p[0], p[1], p[2], p[3]));
+    sts128(sbase + stg_off(r, c0 + 8), make_uint4(p[4], p[5], p[6], p[7]));
   } else if (EPI == EPI_PLAIN) {
     uint32_t p[8];
 #pragma unroll
@@ -384,8 +393,8 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
       p[j] = pack_bf16(lo, hi);
     }
     if (C::STAGED) {
-      *reinterpret_cast<uint4*>(stg + stg_off(r, c0)) = make_uint4(p[0], p[1], p[2], p[3]);
-      *reinterpret_cast<uint4*>(stg + stg_off(r, c0 + 8)) = make_uint4(p[4], p[5], p[6], p[7]);
+      sts128(smem_u32(stg) + stg_off(r, c0), make_uint4(p[0], p[1], p[2], p[3]));
+      sts128(smem_u32(stg) + stg_off(r, c0 + 8), make_uint4(p[4], p[5], p[6], p[7]));
     } else if (row_ok) {
       if (col + 15 < a.N) {
         uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col);
@@ -472,8 +481,8 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + C::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full = empty_bar + C::STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* in_full = tmem_empty + 2;   // staged inputs landed (RES_SKIP)
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint64_t* in_full = tmem_empty + 4;   // staged inputs landed (RES_SKIP)
   uint64_t* in_empty = in_full + 3;     // staging buffer may be overwritten by the next input load
   uint64_t* w_full = in_empty + 3;      // WS: resident weights landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
@@ -513,7 +522,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
       mbar_init(full_bar + i, 1);
       mbar_init(empty_bar + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, C::WPG * (PAIR ? 2 : 1));   // one arrive per warp draining this stage
     }
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
         }
       }
       umma_commit_elect<PAIR>(smem_u32(tmem_full + as));   // accumulator complete -> epilogue (of both CTAs for a pair)
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == C::NACC) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9): two groups of four warps alternate tiles =====================
@@ -645,14 +654,14 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
     double ls_sum = 0.0;
     int m_tile, n_tile;
     for (int it = grp; tile_of(it, m_tile, n_tile); it += C::GROUPS) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1;
+      const int as = it % C::NACC;
+      const uint32_t aphase = (uint32_t)(it / C::NACC) & 1;
       const int ub = m_tile / a.tiles_per_utt;
       const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
       const int t = t0 + r;
       const bool row_ok = t < a.Ti && ub < a.B;
       const int64_t row = (int64_t)ub * a.Ti + t;
-      const int sb = C::IN_PLACE ? it % 3 : as;
+      const int sb = C::IN_PLACE ? it % 3 : grp;
       uint8_t* stg = stg_base + (size_t)sb * C::STG_BYTES;
       bool have_in = false;
       if (C::STAGED) {
@@ -690,6 +699,14 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
             for (int k = 0; k < LDW / 4; ++k) xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        // RES_SKIP: this thread's slice of the staged input tile (already landed: in_full was waited for), fetched with
+        // explicit shared-space loads BEFORE the accumulator wait so their latency overlaps it
+        uint4 inp[LDW >= 8 ? LDW / 8 : 1];
+        if (EPI == EPI_RES_SKIP && have_in) {
+          const uint32_t sbase = smem_u32(stg);
+#pragma unroll
+          for (int k = 0; k < LDW / 8; ++k) inp[k] = lds128(sbase + stg_off(r, cc + 8 * k));
+        }
 #pragma unroll
         for (int j = 0; j < LDW; j += 16) tmem_ld_x16(taddr + cc + j, v + j);
         tmem_ld_wait();
@@ -702,7 +719,8 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < LDW; j += 16) epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cc + j, v + j, stg, have_in, sbias, ls_sum);
+          for (int j = 0; j < LDW; j += 16)
+            epilogue16<EPI, BN, WS>(a, row, row_ok, r, n_tile, cc + j, v + j, stg, have_in, inp + j / 8, sbias, ls_sum);
         }
       }
       tcgen05_fence_before();
