@@ -267,6 +267,12 @@ def main():
             "families": {k: {"ms": v[0], "launches": v[1], "achieved": (v[2] / (v[0] * 1e-3) / (1e9 if k == "upsample" else 1e12)) if v[0] > 0 else 0.0,
                              "unit": "GB/s" if k == "upsample" else "TFLOP/s"} for k, v in prof.items()},
             "whole_pass_tflops": value * MFLOP_PER_SAMPLE[preset] * 1e6 / 1e12 / world}
+    tp = os.path.join(ROOT, "profiles", "r1_gate_traffic.json")
+    if dtype == "bfloat16" and args.workload == "c3" and os.path.exists(tp):
+        tj = json.load(open(tp))
+        # DRAM bytes of ONE ncu --set full capture of this kernel (its block-0 launch), next to that launch's algorithmic bytes
+        roof["traffic"] = tj["traffic_bytes_per_launch"]
+        roof["traffic_detail"] = {k: tj[k] for k in ("launch", "source", "algorithmic_bytes_per_launch", "algorithmic_flop_per_launch")}
     ups = prof["upsample"]
     if ups[0] > 0:
         roof["upsample_hbm_frac"] = ups[2] / (ups[0] * 1e-3) / 1e9 / pk["hbm_gbs"]
