@@ -1,7 +1,11 @@
 // Engine dispatch: which implicit-GEMM kernel family executes the WaveNet contractions.
-//   FWN_FP32       -> CUDA-core fp32 engine (conv_simt.cu), the parity mode
+//   FWN_FP32       -> the parity mode: 3-way bf16-split tcgen05 engine (gemm_tc3.cu, fp32-GEMM accuracy) for the WaveNet GEMMs;
+//                     CUDA-core fp32 engine (conv_simt.cu) for the front conv and when FWN_FP32_ENGINE=simt
 //   FWN_MIXED_BF16 -> tcgen05/TMEM/TMA engine (gemm_tc.cu), the throughput mode
 // There is no cross-fallback: a mode either runs on its engine or fails.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "model.h"
 
@@ -10,6 +14,18 @@ namespace fwn {
 int tc_prepare(Model* m, const Workspace& w, int B, int T, cudaStream_t st);
 int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPack& fp, cudaStream_t st);
 void tc_free(Model* m);
+bool tc3_supported(const GemmArgs& g);
+int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, cudaStream_t st);
+
+// FWN_FP32_ENGINE = tc3 (default) | simt
+static bool fp32_split_engine() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_FP32_ENGINE");
+    v = (e && !strcmp(e, "simt")) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int prepare_engine(Model* m, const Workspace& w, int B, int T, cudaStream_t st) {
   if (m->cfg.precision == FWN_FP32) return 0;
@@ -18,7 +34,11 @@ int prepare_engine(Model* m, const Workspace& w, int B, int T, cudaStream_t st) 
 
 int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPack& fp, cudaStream_t st) {
   m->launches++;
-  if (m->cfg.precision == FWN_FP32) return simt_gemm(g, kind, st);
+  if (m->cfg.precision == FWN_FP32) {
+    const W3& w3 = fp.w3[gemm_id];
+    if (w3.p && fp32_split_engine() && tc3_supported(g)) return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, st);
+    return simt_gemm(g, kind, st);
+  }
   return tc_run(m, g, kind, gemm_id, fp, st);
 }
 

@@ -1,0 +1,90 @@
+// fp32 epilogues of the implicit GEMM, shared by the two engines of the fp32 parity mode (CUDA-core engine in conv_simt.cu and the
+// 3-way-split tcgen05 engine in gemm_tc3.cu).  Called with 4 consecutive accumulator columns (col % 4 == 0) of one row.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fwn {
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------- epilogues (fp32 activations)
+// Called with 4 consecutive columns (col % 4 == 0) of one row.
+template <int EPI>
+struct Epilogue {
+  __device__ static __forceinline__ void apply(const GemmArgs& g, int64_t row, int t, int col, const float acc[4], double& ls_sum) {
+    const EpiArgs& e = g.e;
+    if (EPI == EPI_PLAIN) {
+      float* y = reinterpret_cast<float*>(e.out0) + row * e.ld;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = col + j;
+        if (n < g.N) {
+          float v = acc[j];
+          if (e.colscale) v *= __ldg(e.colscale + n);
+          v += __ldg(e.bias + n);
+          y[n] = e.relu ? fmaxf(v, 0.f) : v;
+        }
+      }
+    } else if (EPI == EPI_GATE) {
+      // columns (2c, 2c+1) = (filter_c, gate_c)  -> o[row, c] = tanh(f) * sigmoid(g)   (modules.py:124)
+      float* o = reinterpret_cast<float*>(e.out0) + row * e.F;
+      if (col + 3 < g.N) {
+        float f0 = acc[0] + __ldg(e.bias + col), g0 = acc[1] + __ldg(e.bias + col + 1);
+        float f1 = acc[2] + __ldg(e.bias + col + 2), g1 = acc[3] + __ldg(e.bias + col + 3);
+        float2 v = make_float2(tanhf(f0) * sigmoidf_acc(g0), tanhf(f1) * sigmoidf_acc(g1));
+        *reinterpret_cast<float2*>(o + col / 2) = v;
+      }
+    } else if (EPI == EPI_RES_SKIP) {
+      // [0,F): h_out = (h_in + res) * sqrt(.5) (modules.py:128); skip columns: skip (+ running sum) (modules.py:127,176)
+      const int F = e.F;
+      if (col + 3 < g.N) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+        float v[4] = {acc[0] + b4.x, acc[1] + b4.y, acc[2] + b4.z, acc[3] + b4.w};
+        if (e.has_res && col < F) {
+          const float4 h = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.in0) + row * F + col));
+          const float s = 0.70710678118654752440f;
+          float4 r = make_float4((h.x + v[0]) * s, (h.y + v[1]) * s, (h.z + v[2]) * s, (h.w + v[3]) * s);
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out0) + row * F + col) = r;
+        } else {
+          const int c = e.has_res ? col - F : col;
+          if (e.in1) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.in1) + row * F + c));
+            v[0] += s4.x; v[1] += s4.y; v[2] += s4.z; v[3] += s4.w;
+          }
+          if (e.relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out1) + row * F + c) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    } else if (EPI == EPI_AFFINE) {
+      // columns (2q, 2q+1) = (log_s, t) of transformed element q; also applies ActNorm to both halves.
+      float* xr = e.X + row * e.Cx;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int q = col / 2 + p;
+        if (q >= e.nq) continue;
+        const float log_s = acc[2 * p] + __ldg(e.bias + col + 2 * p);
+        const float tt = acc[2 * p + 1] + __ldg(e.bias + col + 2 * p + 1);
+        const int oa = __ldg(e.a_off + q), ob = __ldg(e.b_off + q);
+        float xa = xr[oa], xb = xr[ob];
+        if (!e.reverse) {  // Flow.forward: ActNorm, then out_b = (in_b - t) exp(-log_s)   (model.py:188-189,134)
+          xa = (xa + __ldg(e.an_b + oa)) * __ldg(e.an_s + oa);
+          xb = (xb + __ldg(e.an_b + ob)) * __ldg(e.an_s + ob);
+          xb = (xb - tt) * expf(-log_s);
+          ls_sum += (double)log_s;
+        } else {           // Flow.reverse: in_b = out_b exp(log_s) + t, then ActNorm.reverse   (model.py:156,201)
+          xb = xb * expf(log_s) + tt;
+          xa = xa * __ldg(e.an_s + oa) - __ldg(e.an_b + oa);
+          xb = xb * __ldg(e.an_s + ob) - __ldg(e.an_b + ob);
+        }
+        xr[oa] = xa;
+        xr[ob] = xb;
+      }
+    }
+  }
+};
+
+}  // namespace fwn

@@ -46,6 +46,12 @@ int num_sms() {
   return n;
 }
 
+static float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 static uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -205,6 +211,30 @@ static size_t store_matrix(Bump& b, const std::vector<double>& w, int K, int N, 
   *ld_out = Kpad;
   return off;
 }
+// fp32 mode: additionally the three bf16 planes of the split engine, [3][Npad][Kpad] (K-major B operands).
+struct W3Off { size_t off; int Kpad, Npad; bool set = false; };
+static W3Off store_planes(Bump& b, const std::vector<double>& w, int K, int N) {
+  W3Off o;
+  o.Kpad = (K + 63) / 64 * 64;
+  o.Npad = (N + 15) / 16 * 16;
+  const size_t plane = (size_t)o.Kpad * o.Npad;
+  o.off = b.alloc(3 * plane * 2);
+  uint16_t* d = reinterpret_cast<uint16_t*>(b.buf.data() + o.off);
+  memset(d, 0, 3 * plane * 2);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float x = (float)w[(size_t)k * N + n];   // the fp32 value the CUDA-core engine would use
+      const uint16_t h1 = f2bf(x);
+      const float r1 = x - bf2f(h1);
+      const uint16_t h2 = f2bf(r1);
+      const float r2 = r1 - bf2f(h2);
+      const uint16_t h3 = f2bf(r2);
+      const size_t i = (size_t)n * o.Kpad + k;
+      d[i] = h1; d[plane + i] = h2; d[2 * plane + i] = h3;
+    }
+  o.set = true;
+  return o;
+}
 static size_t store_floats(Bump& b, const std::vector<double>& v, int pad_to = 0) {
   size_t n = std::max<size_t>(v.size(), (size_t)pad_to);
   size_t off = b.alloc(n * 4);
@@ -236,6 +266,7 @@ int model_prepack(Model* m, cudaStream_t st) {
   struct FlowOff {  // offsets into the staging buffer, turned into device pointers after upload
     size_t a_off, b_off, off2log, an_b, an_s, an_is, front_w, front_b, front_wtc, final_w, final_b, zero_w, zero_b;
     std::vector<size_t> gate_w, gate_b, rs_w, rs_b;
+    W3Off w3[GEMM_IDS];
   };
   std::vector<FlowOff> offs;
   m->flows.clear();
@@ -373,6 +404,7 @@ int model_prepack(Model* m, cudaStream_t st) {
         }
         int ld;
         fo.gate_w.push_back(store_matrix(b, W, Kg, Ng, bf16, &ld));
+        if (!bf16) fo.w3[GEMM_GATE0 + n] = store_planes(b, W, Kg, Ng);
         fp.gate_ld = ld;
         fo.gate_b.push_back(store_floats(b, B));
         // res | skip 1x1 (the last layer's residual output is dead in the reference graph: modules.py:170-176)
@@ -395,6 +427,7 @@ int model_prepack(Model* m, cudaStream_t st) {
           else B2[ch] = bs[ch];
         }
         fo.rs_w.push_back(store_matrix(b, W2, F, Nr, bf16, &ld));
+        if (!bf16) fo.w3[GEMM_RS0 + n] = store_planes(b, W2, F, Nr);
         fp.rs_ld[n] = ld;
         fo.rs_b.push_back(store_floats(b, B2));
       }
@@ -402,6 +435,7 @@ int model_prepack(Model* m, cudaStream_t st) {
         std::vector<double> w = wn_kernel(hp, wpre + "/Conv_final/conv1d", 1, F, F);
         int ld;
         fo.final_w = store_matrix(b, w, F, F, bf16, &ld);
+        if (!bf16) fo.w3[GEMM_FINAL] = store_planes(b, w, F, F);
         fp.final_ld = ld;
         const float* bb = hp.p(wpre + "/Conv_final/conv1d/bias");
         fo.final_b = store_floats(b, std::vector<double>(bb, bb + F));
@@ -434,6 +468,7 @@ int model_prepack(Model* m, cudaStream_t st) {
         }
         int ld;
         fo.zero_w = store_matrix(b, W, F, Nz, bf16, &ld);
+        if (!bf16) fo.w3[GEMM_ZERO] = store_planes(b, W, F, Nz);
         fp.zero_ld = ld;
         fo.zero_b = store_floats(b, B, (Nz + 15) / 16 * 16);
       }
@@ -477,6 +512,7 @@ int model_prepack(Model* m, cudaStream_t st) {
     fp.final_b = reinterpret_cast<float*>(base + fo.final_b);
     fp.zero_w = base + fo.zero_w;
     fp.zero_b = reinterpret_cast<float*>(base + fo.zero_b);
+    for (int i = 0; i < GEMM_IDS; ++i) fp.w3[i] = W3{fo.w3[i].set ? (void*)(base + fo.w3[i].off) : nullptr, fo.w3[i].Kpad, fo.w3[i].Npad};
     for (int n = 0; n < L; ++n) {
       fp.gate_w[n] = base + fo.gate_w[n];
       fp.gate_b[n] = reinterpret_cast<float*>(base + fo.gate_b[n]);

@@ -21,6 +21,12 @@ struct ParamDesc {
 
 constexpr int MAX_LAYERS = 8;
 
+enum GemmId { GEMM_GATE0 = 0, GEMM_RS0 = MAX_LAYERS, GEMM_FINAL = 2 * MAX_LAYERS, GEMM_ZERO = 2 * MAX_LAYERS + 1, GEMM_FRONT = 2 * MAX_LAYERS + 2,
+              GEMM_IDS = 2 * MAX_LAYERS + 3 };
+
+// fp32 mode, split engine: the [K][N] matrix as three bf16 planes [3][Npad][Kpad] (w = w1 + w2 + w3), see gemm_tc3.cu
+struct W3 { void* p; int Kpad, Npad; };
+
 // Prepacked weights of one flow (ActNorm + AffineCoupling/WaveNet), device pointers.
 struct FlowPack {
   int Cx, nq, Kc, cond_half;
@@ -36,6 +42,7 @@ struct FlowPack {
   void* final_w; float* final_b;
   void* zero_w;  float* zero_b;
   int gate_ld, rs_ld[MAX_LAYERS], final_ld, zero_ld;
+  W3 w3[GEMM_IDS];   // indexed by GemmId; p == nullptr when absent (mixed mode, front conv)
 };
 
 struct Workspace {
@@ -48,8 +55,6 @@ struct Workspace {
   size_t bytes;
 };
 
-enum GemmId { GEMM_GATE0 = 0, GEMM_RS0 = MAX_LAYERS, GEMM_FINAL = 2 * MAX_LAYERS, GEMM_ZERO = 2 * MAX_LAYERS + 1, GEMM_FRONT = 2 * MAX_LAYERS + 2,
-              GEMM_IDS = 2 * MAX_LAYERS + 3 };
 
 struct TcPlan;  // tensor maps of the tcgen05 engine (gemm_tc.cu)
 
