@@ -98,6 +98,32 @@ int fwn_profile_enable(fwn_handle h, int on);
 int fwn_profile_read(fwn_handle h, double ms[8], int64_t launches[8], double work[8]);
 int fwn_receptive_halo(fwn_handle h); /* samples of halo per side needed for exact chunked synthesis */
 
+/* ---- training step: train.py:56-81 (loss, tf.gradients, tower average, clip, Adam), train.py:15-24 (lr) ----
+ * fp32 models only.  The variable vector is flat: variable i of fwn_param_info occupies floats
+ * [fwn_param_offset(i), +numel) of a buffer of fwn_param_floats(h) floats; gradients use the same layout. */
+/* Build the training state (gather maps, transposed operands, Adam moments).  Call after the last fwn_set_param, instead of or
+ * after fwn_prepack. */
+int fwn_train_enable(fwn_handle h, void* stream);
+int64_t fwn_train_workspace_bytes(fwn_handle h, int B, int T);
+int64_t fwn_param_floats(fwn_handle h);
+int64_t fwn_param_offset(fwn_handle h, int index);
+int64_t fwn_grad_floats(fwn_handle h); /* >= fwn_param_floats: the tail is scratch of the backward pass */
+int fwn_params_ptr(fwn_handle h, float** dev_ptr); /* the flat variable vector itself (device, owned by the handle) */
+/* One tower of build_model (train.py:56-66): log_p, logdet = model.forward(x, c, g); grads = d(-(log_p + logdet))/d variables.
+ * grads: device buffer of grad_floats >= fwn_grad_floats(h) floats, overwritten.  Variables the loss does not depend on
+ * (speaker_embeddings: the reference's tf.gradients returns None for them, train.py:75 filters them out) get zero. */
+int fwn_loss_and_grads(fwn_handle h, const float* x, const float* c, const int32_t* g, int B, int T, float* logp_out,
+                       float* logdet_out, float* grads, int64_t grad_floats, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+/* tf.global_norm of the gradient vector (train.py:29) -> device scalar */
+int fwn_grad_global_norm(fwn_handle h, const float* grads, float* norm_out, void* stream);
+/* clip_by_global_norm(clip_norm) + tf.train.AdamOptimizer.apply_gradients (train.py:27-31,76-81) + device-side re-pack of every
+ * derived operand.  `grads` = the tower average (utils.py:34-60), computed by the caller (all-reduce).  step counts from 1. */
+int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm,
+                        int64_t step, void* stream);
+/* Device-side twin of fwn_prepack (needs fwn_train_enable): re-derive all operands from the current variables. */
+int fwn_repack(fwn_handle h, void* stream);
+
 /* ---- per-op entry points (reference layout, fp32): one per TF op site of SURVEY 2.3 ---- */
 /* Block.forward squeeze model.py:226-228: y[b,t,2c+k] = x[b,2t+k,c];  x [B,T,C] -> y [B,T/2,2C] */
 int fwn_squeeze(const float* x, float* y, int B, int T, int C, void* stream);

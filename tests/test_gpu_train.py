@@ -1,0 +1,119 @@
+"""Training step through the C ABI (fwn_train_enable / fwn_loss_and_grads / fwn_apply_gradients) against the
+training oracle: gradients of -(log_p + logdet) w.r.t. EVERY variable, the device-side re-pack, clip + Adam trajectories.
+Tolerance (stated): every variable's gradient within 5e-4 of its own max-abs (fp32 accumulation, float64 referee)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flowavenet_oracle as O
+from oracle import flowavenet_train_oracle as TO
+from tests._golden import load
+from tests.test_gpu_model import make_model
+
+pytestmark = pytest.mark.gpu
+
+GRAD_CASES = ["g1_b2f2l2", "g2_b3f2l1", "g4_causal", "g5_additive", "g6_l3"]
+
+
+def check_grads(got, ref, tol=5e-4):
+    gmax = max(float(r.abs().max()) for r in ref.values())
+    worst = ("", 0.0)
+    for k, r in ref.items():
+        g = got[k].double().cpu()
+        r = r.double()
+        scale = max(float(r.abs().max()), 1e-6 * gmax)
+        err = float((g - r).abs().max()) / scale
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < tol, worst
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_gradients_match_oracle(case):
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load(case)
+    net = make_model(hp, params)
+    tr = T.Trainer(net)
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    log_p, logdet = tr.loss_and_grads(x, c)
+    np.testing.assert_allclose(float(log_p), float(fx["log_p"]), rtol=1e-4)
+    np.testing.assert_allclose(float(logdet), float(fx["logdet"]), rtol=1e-4, atol=1e-6)
+    _, _, _, ref = TO.loss_and_grads(params, hp, torch.from_numpy(fx["x"]), torch.from_numpy(fx["c"]))
+    check_grads(tr.gradients(), ref)
+    # deterministic up to atomics: a second call agrees to fp32 rounding
+    g1 = tr.grads.clone()
+    tr.loss_and_grads(x, c)
+    assert float((tr.grads - g1).abs().max()) <= 1e-4 * float(g1.abs().max())
+
+
+def test_device_repack_equals_host_prepack():
+    """fwn_train_enable re-derives every operand on the device; the forward result must stay on the golden values, and a
+    forward in inference mode after it (same handle) as well."""
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load("g1_b2f2l2")
+    net = make_model(hp, params)
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    T.Trainer(net)
+    log_p, logdet, z = net.forward(x, c, return_z=True)
+    np.testing.assert_allclose(float(log_p), float(fx["log_p"]), rtol=1e-4)
+    np.testing.assert_allclose(float(logdet), float(fx["logdet"]), rtol=1e-4, atol=1e-6)
+    assert float(np.abs(z.cpu().numpy() - fx["z"]).max() / np.abs(fx["z"]).max()) < 1e-4
+
+
+def test_training_trajectory_matches_oracle():
+    """Three optimizer steps (clip_by_global_norm 1 + Adam 1e-3, train.py:15-32,76-81) against the float64 oracle."""
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load("g1_b2f2l2")
+    net = make_model(hp, params)
+    tr = T.Trainer(net)
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    p = {k: v.double() for k, v in params.items()}
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v = {k: torch.zeros_like(v) for k, v in p.items()}
+    p0 = {k: t.clone() for k, t in p.items()}
+    for step in range(3):
+        info = tr.train_step(x, c)
+        p, ref = TO.train_step(p, hp, [(torch.from_numpy(fx["x"]), torch.from_numpy(fx["c"]))], m, v, step)
+        assert abs(float(info["loss"]) - ref["loss"]) < 1e-4 * max(1.0, abs(ref["loss"])), (step, float(info["loss"]), ref["loss"])
+        np.testing.assert_allclose(float(info["grad_global_norm"]), ref["grad_global_norm"], rtol=1e-3)
+        assert info["learning_rate"] == ref["lr"]
+    got = tr.variables()
+    lr = 1e-3
+    dev, tot = 0.0, 0
+    for k in p:
+        d_ref = (p[k] - p0[k])
+        d_got = got[k].double().cpu() - p0[k]
+        # Adam normalises each coordinate: coordinates with |g| ~ eps are ill-conditioned, so bound the mean deviation
+        dev += float((d_got - d_ref).abs().sum())
+        tot += d_ref.numel()
+        assert float((d_got - d_ref).abs().max()) <= 3 * lr * 3 + 1e-7, k
+    assert dev / tot < 0.02 * lr, dev / tot
+    # the loss went down
+    lp, ld = net.forward(x, c)
+    assert float(-(lp + ld)) < float(-(fx["log_p"] + fx["logdet"]))
+
+
+def test_init_step_runs_ddi_then_trains():
+    """train.py:221,229: the first sess.run feeds init=True -- ActNorm statistics from the batch, then a normal update."""
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load("g1_b2f2l2")
+    net = make_model(hp, params)
+    tr = T.Trainer(net)
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    info = tr.train_step(x, c, init=True)
+    np.testing.assert_allclose(float(info["log_p"]), float(fx["ddi_log_p"]), rtol=1e-4)
+    np.testing.assert_allclose(float(info["logdet"]), float(fx["ddi_logdet"]), rtol=1e-4)
+    pd = O.ddi_init({k: v.double() for k, v in params.items()}, hp, torch.from_numpy(fx["x"]), torch.from_numpy(fx["c"]), torch.float64)
+    _, _, _, ref = TO.loss_and_grads(pd, hp, torch.from_numpy(fx["x"]), torch.from_numpy(fx["c"]))
+    # gradient of the init step is taken at the DDI values
+    tr2 = T.Trainer(make_model(hp, {k: v.float() for k, v in pd.items()}))
+    tr2.loss_and_grads(x, c)
+    check_grads(tr2.gradients(), ref)
+
+
+def test_training_needs_fp32_and_enable():
+    import tf_flowavenet_b200 as P
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load("g1_b2f2l2")
+    with pytest.raises(ValueError):
+        T.Trainer(make_model(hp, params, dtype="bfloat16"))

@@ -38,6 +38,16 @@ SIGNATURES = {
     "fwn_forward_host": (_i, [_p, _fp, _fp, _fp, _i, _i, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fwn_reverse_host": (_i, [_p, _fp, _fp, _fp, _i, _i, _fp]),
     "fwn_reverse_chunk": (_i, [_p, _fp, _fp, _i, _i, _i, _i, _fp, _p, _l, _p]),
+    "fwn_train_enable": (_i, [_p, _p]),
+    "fwn_train_workspace_bytes": (_l, [_p, _i, _i]),
+    "fwn_param_floats": (_l, [_p]),
+    "fwn_param_offset": (_l, [_p, _i]),
+    "fwn_grad_floats": (_l, [_p]),
+    "fwn_params_ptr": (_i, [_p, C.POINTER(_p)]),
+    "fwn_loss_and_grads": (_i, [_p, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _l, _p, _l, _p]),
+    "fwn_grad_global_norm": (_i, [_p, _fp, _fp, _p]),
+    "fwn_apply_gradients": (_i, [_p, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _l, _p]),
+    "fwn_repack": (_i, [_p, _p]),
     "fwn_last_launches": (_l, [_p]),
     "fwn_profile_enable": (_i, [_p, _i]),
     "fwn_profile_read": (_i, [_p, C.POINTER(C.c_double * 8), C.POINTER(_l * 8), C.POINTER(C.c_double * 8)]),

@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "model.h"
+#include "train.h"
 
 using namespace fwn;
 
@@ -141,6 +142,51 @@ int fwn_reverse(fwn_handle h, const float* z, const float* c, const int32_t* g, 
   FWN_CHECK(h, "null handle");
   h->m->launches = 0;
   return model_reverse(h->m, z, c, g, B, T, x_out, workspace, workspace_bytes, S(stream));
+}
+
+// ---- training step (train.cu)
+int fwn_train_enable(fwn_handle h, void* stream) {
+  FWN_CHECK(h, "null handle");
+  return train_enable(h->m, S(stream));
+}
+int64_t fwn_train_workspace_bytes(fwn_handle h, int B, int T) {
+  if (!h) {
+    set_error("null handle");
+    return -1;
+  }
+  return train_workspace_bytes(h->m, B, T);
+}
+int64_t fwn_param_floats(fwn_handle h) { return h ? h->m->raw_floats : -1; }
+int64_t fwn_grad_floats(fwn_handle h) { return h ? train_grad_floats(h->m) : -1; }
+int64_t fwn_param_offset(fwn_handle h, int index) {
+  if (!h || index < 0 || index >= (int)h->m->params.size()) {
+    set_error("fwn_param_offset: bad handle or index");
+    return -1;
+  }
+  return h->m->params[index].offset;
+}
+int fwn_params_ptr(fwn_handle h, float** dev_ptr) {
+  FWN_CHECK(h && dev_ptr, "null argument");
+  *dev_ptr = h->m->raw;
+  return 0;
+}
+int fwn_loss_and_grads(fwn_handle h, const float* x, const float* c, const int32_t* g, int B, int T, float* logp_out, float* logdet_out,
+                       float* grads, int64_t grad_floats, void* workspace, int64_t workspace_bytes, void* stream) {
+  FWN_CHECK(h, "null handle");
+  return train_loss_and_grads(h->m, x, c, g, B, T, logp_out, logdet_out, grads, grad_floats, workspace, workspace_bytes, S(stream));
+}
+int fwn_grad_global_norm(fwn_handle h, const float* grads, float* norm_out, void* stream) {
+  FWN_CHECK(h && grads && norm_out, "null argument");
+  return train_grad_norm(h->m, grads, norm_out, S(stream));
+}
+int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm, int64_t step,
+                        void* stream) {
+  FWN_CHECK(h && grads, "null argument");
+  return train_apply(h->m, grads, lr, beta1, beta2, eps, clip_norm, step, S(stream));
+}
+int fwn_repack(fwn_handle h, void* stream) {
+  FWN_CHECK(h, "null handle");
+  return train_repack(h->m, S(stream));
 }
 
 int64_t fwn_last_launches(fwn_handle h) { return h ? h->m->launches : -1; }

@@ -1,5 +1,6 @@
 // Shared helpers for libflowavenet_b200 (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -29,7 +30,20 @@ const char* get_error();
     }                                                                                        \
   } while (0)
 
-#define FWN_LAUNCH_CHECK() FWN_CUDA(cudaGetLastError())
+// FWN_SYNC_DEBUG=1 synchronises after every launch so an asynchronous fault is reported at the kernel that caused it
+inline cudaError_t launch_status() {
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("FWN_SYNC_DEBUG");
+    dbg = (e && e[0] == '1') ? 1 : 0;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && dbg) {
+    e = cudaDeviceSynchronize();
+  }
+  return e;
+}
+#define FWN_LAUNCH_CHECK() FWN_CUDA(::fwn::launch_status())
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -154,6 +154,8 @@ int simt_gemm(const GemmArgs& a, EpiKind kind, cudaStream_t st) {
     case EPI_GATE: simt_gemm_kernel<EPI_GATE><<<grid, NT, 0, st>>>(a); break;
     case EPI_RES_SKIP: simt_gemm_kernel<EPI_RES_SKIP><<<grid, NT, 0, st>>>(a); break;
     case EPI_AFFINE: simt_gemm_kernel<EPI_AFFINE><<<grid, NT, 0, st>>>(a); break;
+    case EPI_LINEAR: simt_gemm_kernel<EPI_LINEAR><<<grid, NT, 0, st>>>(a); break;
+    case EPI_GATE_BWD: simt_gemm_kernel<EPI_GATE_BWD><<<grid, NT, 0, st>>>(a); break;
   }
   FWN_LAUNCH_CHECK();
   return 0;

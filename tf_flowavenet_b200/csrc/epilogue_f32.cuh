@@ -34,6 +34,8 @@ struct Epilogue {
         float f1 = acc[2] + __ldg(e.bias + col + 2), g1 = acc[3] + __ldg(e.bias + col + 3);
         float2 v = make_float2(tanhf(f0) * sigmoidf_acc(g0), tanhf(f1) * sigmoidf_acc(g1));
         *reinterpret_cast<float2*>(o + col / 2) = v;
+        if (e.out1)  // training: keep the pre-activations for the backward pass
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out1) + row * (2 * e.F) + col) = make_float4(f0, g0, f1, g1);
       }
     } else if (EPI == EPI_RES_SKIP) {
       // [0,F): h_out = (h_in + res) * sqrt(.5) (modules.py:128); skip columns: skip (+ running sum) (modules.py:127,176)
@@ -69,6 +71,7 @@ struct Epilogue {
         const float log_s = acc[2 * p] + __ldg(e.bias + col + 2 * p);
         const float tt = acc[2 * p + 1] + __ldg(e.bias + col + 2 * p + 1);
         const int oa = __ldg(e.a_off + q), ob = __ldg(e.b_off + q);
+        if (e.out1) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.out1) + row * e.ld + 2 * q) = make_float2(log_s, tt);
         float xa = xr[oa], xb = xr[ob];
         if (!e.reverse) {  // Flow.forward: ActNorm, then out_b = (in_b - t) exp(-log_s)   (model.py:188-189,134)
           xa = (xa + __ldg(e.an_b + oa)) * __ldg(e.an_s + oa);
@@ -82,6 +85,39 @@ struct Epilogue {
         }
         xr[oa] = xa;
         xr[ob] = xb;
+      }
+    } else if (EPI == EPI_LINEAR) {
+      float* y = reinterpret_cast<float*>(e.out0) + row * e.ld;
+      const float* a0 = e.in0 ? reinterpret_cast<const float*>(e.in0) + row * e.ld : nullptr;
+      const float* mk = e.in1 ? reinterpret_cast<const float*>(e.in1) + row * e.ld : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = col + j;
+        if (n < g.N) {
+          float v = acc[j];
+          if (e.bias) v += __ldg(e.bias + n);
+          if (a0) v += a0[n];
+          v *= e.alpha;
+          if (mk && !(mk[n] > 0.f)) v = 0.f;
+          y[n] = v;
+        }
+      }
+    } else if (EPI == EPI_GATE_BWD) {
+      // o = tanh(f) sigmoid(g):  df = do sigmoid(g) (1 - tanh^2 f),  dg = do tanh(f) sigmoid(g) (1 - sigmoid(g))
+      if (col + 3 < g.N) {
+        const float* fg = reinterpret_cast<const float*>(e.in0) + row * (2 * e.F) + 2 * col;
+        float* d = reinterpret_cast<float*>(e.out0) + row * (2 * e.F) + 2 * col;
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(fg)), p1 = __ldg(reinterpret_cast<const float4*>(fg + 4));
+        const float pf[4] = {p0.x, p0.z, p1.x, p1.z}, pg[4] = {p0.y, p0.w, p1.y, p1.w};
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float th = tanhf(pf[j]), sg = sigmoidf_acc(pg[j]);
+          r[2 * j] = acc[j] * sg * (1.f - th * th);
+          r[2 * j + 1] = acc[j] * th * sg * (1.f - sg);
+        }
+        *reinterpret_cast<float4*>(d) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(r[4], r[5], r[6], r[7]);
       }
     }
   }

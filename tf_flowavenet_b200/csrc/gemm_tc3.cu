@@ -15,6 +15,7 @@
 //   warp 1      MMA: six tcgen05.mma groups (one per split term) into the TMEM accumulator, commit frees stage + operand tiles
 //   warps 6-13  epilogue: two groups alternate tiles; tcgen05.ld, then the SAME fp32 epilogue functor as the CUDA-core engine
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -281,7 +282,7 @@ static int launch(const Tc3Args& a, cudaStream_t st) {
 bool tc3_supported(const GemmArgs& g) {
   if (g.e.colscale) return false;
   for (int s = 0; s < g.nseg; ++s)
-    if ((g.seg[s].lda & 3) || (reinterpret_cast<uintptr_t>(g.seg[s].A) & 15) || g.seg[s].K <= 0) return false;
+    if ((g.seg[s].lda & 3) || (reinterpret_cast<uintptr_t>(g.seg[s].A) & 15) || g.seg[s].K <= 0 || (g.seg[s].koff & 7)) return false;
   return true;
 }
 
@@ -323,11 +324,20 @@ int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad
   }
   a.tiles_per_utt = (g.Ti + tc::BM - 1) / tc::BM;
   a.n_tiles = (g.N + tc3::BN3 - 1) / tc3::BN3;
+  if (getenv("FWN_TC3_TRACE")) {
+    fprintf(stderr, "tc3 kind=%d B=%d Ti=%d N=%d Kpad=%d Npad=%d nseg=%d:", (int)kind, g.B, g.Ti, g.N, Kpad, Npad, g.nseg);
+    for (int s = 0; s < g.nseg; ++s)
+      fprintf(stderr, " [K=%d lda=%lld sh=%d koff=%d nch=%d lk=%d]", g.seg[s].K, (long long)g.seg[s].lda, g.seg[s].shift, g.seg[s].koff,
+              a.nchunk[s], a.last_ksteps[s]);
+    fprintf(stderr, "\n");
+  }
   switch (kind) {
     case EPI_PLAIN: return tc3::launch<EPI_PLAIN>(a, st);
     case EPI_GATE: return tc3::launch<EPI_GATE>(a, st);
     case EPI_RES_SKIP: return tc3::launch<EPI_RES_SKIP>(a, st);
     case EPI_AFFINE: return tc3::launch<EPI_AFFINE>(a, st);
+    case EPI_LINEAR: return tc3::launch<EPI_LINEAR>(a, st);
+    case EPI_GATE_BWD: return tc3::launch<EPI_GATE_BWD>(a, st);
   }
   return 1;
 }

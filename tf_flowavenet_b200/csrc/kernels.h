@@ -34,19 +34,24 @@ struct Seg {
   int koff;        // first W row of this segment
 };
 
-enum EpiKind { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RES_SKIP = 2, EPI_AFFINE = 3 };
+enum EpiKind { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RES_SKIP = 2, EPI_AFFINE = 3,
+               // backward pass (fp32 engines only):
+               EPI_LINEAR = 4,    // y = alpha * (acc + bias? + in0?), optionally masked by (in1 > 0)  (dgrad of the 1x1 / dilated convs)
+               EPI_GATE_BWD = 5   // acc = dL/do -> (dL/df, dL/dg) interleaved, from the saved pre-activations (modules.py:124)
+};
 
 struct EpiArgs {
   const float* bias;       // [N]
   const float* colscale;   // [N] or null (PLAIN: acc*colscale + bias)
   void* out0;              // PLAIN: y; GATE: o [rows,F]; RES_SKIP: h_out [rows,F]
-  void* out1;              // RES_SKIP: skip_out [rows,F]
+  void* out1;              // RES_SKIP: skip_out [rows,F]; training: GATE saves pre-activations [rows,2F], AFFINE saves (log_s,t) [rows,2nq]
   const void* in0;         // RES_SKIP: h_in
   const void* in1;         // RES_SKIP: skip_in (nullable -> no accumulate)
   int64_t ld;              // leading dim of PLAIN output
   int relu;                // PLAIN: relu; RES_SKIP: relu on skip output
   int has_res;             // RES_SKIP: columns [0,F) are the residual conv
   int F;                   // filter size
+  float alpha;             // LINEAR: output scale
   // AFFINE (zero-conv epilogue == ActNorm + coupling in place on the flow variable)
   float* X;                // [rows, Cx] fp32, physical (time-ordered) layout
   int Cx, nq;

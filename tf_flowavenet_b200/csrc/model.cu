@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "model.h"
+#include "train.h"
 
 namespace fwn {
 
@@ -75,10 +76,17 @@ static void add_param(Model* m, const std::string& name, std::vector<int64_t> sh
   m->index[name] = (int)m->params.size();
   m->params.push_back(d);
 }
+static int64_t off_of(const Model* m, const std::string& n) { return m->params[m->index.at(n)].offset; }
 static void add_conv(Model* m, const std::string& p, int k, int cin, int cout) {
   add_param(m, p + "/kernel", {k, cin, cout});
   add_param(m, p + "/wn/g", {cout});
   add_param(m, p + "/bias", {cout});
+  m->folds.push_back(FoldDesc{FOLD_WN, off_of(m, p + "/kernel"), off_of(m, p + "/wn/g"), 0, 0, k * cin, cout});
+}
+static void add_sum2(Model* m, const std::string& a, const std::string& b, int n) {
+  m->ext_of[a] = m->ext_floats;
+  m->folds.push_back(FoldDesc{FOLD_SUM2, off_of(m, a), off_of(m, b), 0, m->ext_floats, 1, n});
+  m->ext_floats += n;
 }
 
 int model_create(const fwn_config* cfg, Model** out) {
@@ -122,14 +130,23 @@ int model_create(const fwn_config* cfg, Model** out) {
         add_conv(m, r + "/conv1d_1", 1, cc / 2, F);  // _gate_conv_c   (modules.py:118)
         add_conv(m, r + "/conv1d_2", 1, F, F);       // _res_conv      (modules.py:126)
         add_conv(m, r + "/conv1d_3", 1, F, F);       // _skip_conv     (modules.py:127)
+        add_sum2(m, r + "/Conv_filter/conv1d/bias", r + "/conv1d/bias", F);
+        add_sum2(m, r + "/Conv_gate/conv1d/bias", r + "/conv1d_1/bias", F);
       }
       add_conv(m, w + "/Conv_final/conv1d", 1, F, F);
       add_param(m, w + "/ZeroConv1d/conv1d/kernel", {1, F, out_ch});
       add_param(m, w + "/ZeroConv1d/conv1d/bias", {out_ch});
       add_param(m, w + "/ZeroConv1d/scale", {1, 1, out_ch});
+      m->folds.push_back(FoldDesc{FOLD_ZERO, off_of(m, w + "/ZeroConv1d/conv1d/kernel"), off_of(m, w + "/ZeroConv1d/conv1d/bias"),
+                                  off_of(m, w + "/ZeroConv1d/scale"), 0, F, out_ch});
     }
   }
   if (cfg->gin_channels > 0) add_param(m, "speaker_embeddings", {cfg->n_speakers, cfg->gin_channels});
+  if (m->raw_floats + m->ext_floats >= (int64_t(1) << 30)) {
+    set_error("model too large for the 30-bit gather map (%lld parameters)", (long long)m->raw_floats);
+    delete m;
+    return 1;
+  }
   cudaError_t e = cudaMalloc(&m->raw, (size_t)m->raw_floats * sizeof(float));
   if (e != cudaSuccess) {
     set_error("cudaMalloc(%lld B) for parameters failed: %s", (long long)m->raw_floats * 4, cudaGetErrorString(e));
@@ -150,6 +167,7 @@ void model_drop_graphs(Model* m) {
 void model_destroy(Model* m) {
   if (!m) return;
   model_drop_graphs(m);
+  train_free(m);
   for (auto e : m->prof_ev) cudaEventDestroy(e);
   cudaFree(m->raw);
   cudaFree(m->pack);
@@ -171,49 +189,104 @@ struct Bump {  // bump allocator over a host staging buffer mirrored 1:1 on the 
   }
 };
 
+// value + provenance of one packed element: `code` = index into the folded parameter vector | sign << 30, -1 = constant zero
+struct Elem { double v; int32_t code; };
+static inline Elem operator-(Elem e) { return Elem{-e.v, e.code < 0 ? e.code : (e.code ^ (1 << 30))}; }
+struct Ref {  // a run of the folded parameter vector
+  const double* w;
+  int64_t base;
+  Elem operator[](size_t i) const { return Elem{w[base + (int64_t)i], (int32_t)(base + (int64_t)i)}; }
+};
+struct PMat {  // a packed matrix / vector being assembled
+  std::vector<double> v;
+  std::vector<int32_t> code;
+  explicit PMat(size_t n = 0) : v(n, 0.0), code(n, -1) {}
+  struct Proxy {
+    PMat* m; size_t i;
+    void operator=(Elem e) { m->v[i] = e.v; m->code[i] = e.code; }
+  };
+  Proxy operator[](size_t i) { return Proxy{this, i}; }
+  Elem at(size_t i) const { return Elem{v[i], code[i]}; }
+  size_t size() const { return v.size(); }
+};
+static PMat pm_from(Ref r, size_t n) {
+  PMat p(n);
+  for (size_t i = 0; i < n; ++i) p[i] = r[i];
+  return p;
+}
+
 struct HostParams {
   const Model* m;
   std::vector<float> raw;
+  std::vector<double> what;  // folded parameter vector (host_fold)
   const float* p(const std::string& n) const {
     auto it = m->index.find(n);
     if (it == m->index.end()) abort();
     return raw.data() + m->params[it->second].offset;
   }
+  Ref ref(const std::string& n) const { return Ref{what.data(), m->params[m->index.at(n)].offset}; }
+  Ref ext(const std::string& first_bias) const { return Ref{what.data(), m->raw_floats + m->ext_of.at(first_bias)}; }
 };
 
-// weight-normed kernel [k][cin][cout] -> doubles (convolutional.py:80: v * rsqrt(max(sum_{k,i} v^2, 1e-12)) * g)
-static std::vector<double> wn_kernel(const HostParams& hp, const std::string& pre, int k, int cin, int cout) {
-  const float* v = hp.p(pre + "/kernel");
-  const float* g = hp.p(pre + "/wn/g");
-  std::vector<double> ss(cout, 0.0), w((size_t)k * cin * cout);
-  for (int64_t r = 0; r < (int64_t)k * cin; ++r)
-    for (int o = 0; o < cout; ++o) ss[o] += (double)v[r * cout + o] * v[r * cout + o];
-  for (int o = 0; o < cout; ++o) ss[o] = (double)g[o] / sqrt(std::max(ss[o], 1e-12));
-  for (int64_t r = 0; r < (int64_t)k * cin; ++r)
-    for (int o = 0; o < cout; ++o) w[r * cout + o] = (double)v[r * cout + o] * ss[o];
-  return w;
+// The fold step on the host, in double precision (the device twin is fold_kernel in train_kernels.cu).
+static void host_fold(HostParams& hp) {
+  const Model* m = hp.m;
+  hp.what.assign((size_t)(m->raw_floats + m->ext_floats), 0.0);
+  for (int64_t i = 0; i < m->raw_floats; ++i) hp.what[i] = hp.raw[i];
+  for (const FoldDesc& d : m->folds) {
+    if (d.kind == FOLD_WN) {  // convolutional.py:80: v * rsqrt(max(sum_{k,i} v^2, 1e-12)) * g
+      const float *v = hp.raw.data() + d.a, *g = hp.raw.data() + d.b;
+      std::vector<double> ss(d.N, 0.0);
+      for (int64_t r = 0; r < d.K; ++r)
+        for (int o = 0; o < d.N; ++o) ss[o] += (double)v[r * d.N + o] * v[r * d.N + o];
+      for (int o = 0; o < d.N; ++o) ss[o] = (double)g[o] / sqrt(std::max(ss[o], 1e-12));
+      for (int64_t r = 0; r < d.K; ++r)
+        for (int o = 0; o < d.N; ++o) hp.what[d.a + r * d.N + o] = (double)v[r * d.N + o] * ss[o];
+    } else if (d.kind == FOLD_ZERO) {
+      for (int o = 0; o < d.N; ++o) {
+        const double e = exp(3.0 * (double)hp.raw[d.c + o]);
+        for (int64_t r = 0; r < d.K; ++r) hp.what[d.a + r * d.N + o] = (double)hp.raw[d.a + r * d.N + o] * e;
+        hp.what[d.b + o] = (double)hp.raw[d.b + o] * e;
+      }
+    } else {
+      for (int j = 0; j < d.N; ++j) hp.what[m->raw_floats + d.d + j] = (double)hp.raw[d.a + j] + (double)hp.raw[d.b + j];
+    }
+  }
 }
+static Ref wn_kernel(const HostParams& hp, const std::string& pre, int, int, int) { return hp.ref(pre + "/kernel"); }
 
-// Store a [K][N] double matrix either as fp32 [K][N] (fp32 engine) or bf16 [Npad][Kpad] (tcgen05 engine, K-major B operand).
-static size_t store_matrix(Bump& b, const std::vector<double>& w, int K, int N, bool bf16, int* ld_out) {
-  if (!bf16) {
-    size_t off = b.alloc((size_t)K * N * 4);
-    float* d = reinterpret_cast<float*>(b.buf.data() + off);
-    for (size_t i = 0; i < (size_t)K * N; ++i) d[i] = (float)w[i];
-    *ld_out = N;
+// fp32 region of the pack buffer: values + gather codes, float-indexed
+struct WBump {
+  std::vector<float> v;
+  std::vector<int32_t> code;
+  size_t alloc(size_t n) {
+    size_t off = (v.size() + 63) & ~size_t(63);
+    v.resize(off + n, 0.f);
+    code.resize(off + n, -1);
     return off;
+  }
+};
+constexpr size_t IN_WALL = size_t(1) << 62;  // tag on offsets that point into the fp32 region
+
+// Store a [K][N] matrix either as fp32 [K][N] in the fp32 region (fp32 engines) or bf16 [Npad][Kpad] (tcgen05 engine, K-major B operand).
+static size_t store_matrix(WBump& bw, Bump& b, const PMat& w, int K, int N, bool bf16, int* ld_out) {
+  if (!bf16) {
+    size_t off = bw.alloc((size_t)K * N);
+    for (size_t i = 0; i < (size_t)K * N; ++i) { bw.v[off + i] = (float)w.v[i]; bw.code[off + i] = w.code[i]; }
+    *ld_out = N;
+    return off | IN_WALL;
   }
   const int Kpad = (K + 63) / 64 * 64, Npad = (N + 15) / 16 * 16;
   size_t off = b.alloc((size_t)Kpad * Npad * 2);
   uint16_t* d = reinterpret_cast<uint16_t*>(b.buf.data() + off);
   for (int n = 0; n < N; ++n)
-    for (int k = 0; k < K; ++k) d[(size_t)n * Kpad + k] = f2bf((float)w[(size_t)k * N + n]);
+    for (int k = 0; k < K; ++k) d[(size_t)n * Kpad + k] = f2bf((float)w.v[(size_t)k * N + n]);
   *ld_out = Kpad;
   return off;
 }
 // fp32 mode: additionally the three bf16 planes of the split engine, [3][Npad][Kpad] (K-major B operands).
 struct W3Off { size_t off; int Kpad, Npad; bool set = false; };
-static W3Off store_planes(Bump& b, const std::vector<double>& w, int K, int N) {
+static W3Off store_planes(Bump& b, const PMat& w, int K, int N) {
   W3Off o;
   o.Kpad = (K + 63) / 64 * 64;
   o.Npad = (N + 15) / 16 * 16;
@@ -223,7 +296,7 @@ static W3Off store_planes(Bump& b, const std::vector<double>& w, int K, int N) {
   memset(d, 0, 3 * plane * 2);
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
-      const float x = (float)w[(size_t)k * N + n];   // the fp32 value the CUDA-core engine would use
+      const float x = (float)w.v[(size_t)k * N + n];   // the fp32 value the CUDA-core engine would use
       const uint16_t h1 = f2bf(x);
       const float r1 = x - bf2f(h1);
       const uint16_t h2 = f2bf(r1);
@@ -234,6 +307,13 @@ static W3Off store_planes(Bump& b, const std::vector<double>& w, int K, int N) {
     }
   o.set = true;
   return o;
+}
+// a (trainable-derived) float vector in the fp32 region
+static size_t store_pvec(WBump& bw, const PMat& v, int pad_to = 0) {
+  size_t n = std::max<size_t>(v.size(), (size_t)pad_to);
+  size_t off = bw.alloc(n);
+  for (size_t i = 0; i < v.size(); ++i) { bw.v[off + i] = (float)v.v[i]; bw.code[off + i] = v.code[i]; }
+  return off | IN_WALL;
 }
 static size_t store_floats(Bump& b, const std::vector<double>& v, int pad_to = 0) {
   size_t n = std::max<size_t>(v.size(), (size_t)pad_to);
@@ -262,7 +342,9 @@ int model_prepack(Model* m, cudaStream_t st) {
   FWN_CUDA(cudaStreamSynchronize(st));
   FWN_CUDA(cudaMemcpy(hp.raw.data(), m->raw, (size_t)m->raw_floats * 4, cudaMemcpyDeviceToHost));
 
+  host_fold(hp);
   Bump b;
+  WBump bw;
   struct FlowOff {  // offsets into the staging buffer, turned into device pointers after upload
     size_t a_off, b_off, off2log, an_b, an_s, an_is, front_w, front_b, front_wtc, final_w, final_b, zero_w, zero_b;
     std::vector<size_t> gate_w, gate_b, rs_w, rs_b;
@@ -362,30 +444,38 @@ int model_prepack(Model* m, cudaStream_t st) {
       fp.cond_half = half;
       // front conv [3][nq][F] (input channel q = logical channel q of x_a)
       {
-        std::vector<double> w = wn_kernel(hp, wpre + "/Conv_front/conv1d", 3, nq, F);
-        fo.front_w = store_floats(b, w);
+        Ref w = wn_kernel(hp, wpre + "/Conv_front/conv1d", 3, nq, F);
+        fo.front_w = store_pvec(bw, pm_from(w, (size_t)3 * nq * F));
+        if (!bf16) {  // split-engine planes: tap k at K rows k*kq8 .. (TMA needs 16-byte aligned K starts)
+          const int kq8 = (nq + 7) / 8 * 8;
+          PMat w3((size_t)3 * kq8 * F);
+          for (int k = 0; k < 3; ++k)
+            for (int q = 0; q < nq; ++q)
+              for (int ch = 0; ch < F; ++ch) w3[((size_t)k * kq8 + q) * F + ch] = w[((size_t)k * nq + q) * F + ch];
+          fo.w3[GEMM_FRONT] = store_planes(b, w3, 3 * kq8, F);
+          fp.front_k16 = kq8;
+        }
         fo.front_wtc = 0;
         if (bf16) {  // tensor-core layout: [3*k16][F] with tap k at rows k*k16 .. k*k16+nq, then transposed to [F][Kpad]
           const int k16 = (nq + 15) / 16 * 16;
-          std::vector<double> wt((size_t)3 * k16 * F, 0.0);
+          PMat wt((size_t)3 * k16 * F);
           for (int k = 0; k < 3; ++k)
             for (int q = 0; q < nq; ++q)
               for (int ch = 0; ch < F; ++ch) wt[((size_t)k * k16 + q) * F + ch] = w[((size_t)k * nq + q) * F + ch];
           int ld;
-          fo.front_wtc = store_matrix(b, wt, 3 * k16, F, true, &ld);
+          fo.front_wtc = store_matrix(bw, b, wt, 3 * k16, F, true, &ld);
           fp.front_ld = ld;
           fp.front_k16 = k16;
         }
-        const float* bb = hp.p(wpre + "/Conv_front/conv1d/bias");
-        fo.front_b = store_floats(b, std::vector<double>(bb, bb + F));
+        fo.front_b = store_pvec(bw, pm_from(hp.ref(wpre + "/Conv_front/conv1d/bias"), F));
       }
       for (int n = 0; n < L; ++n) {
         std::string r = wpre + "/ResBlock_0_" + std::to_string(n);
-        std::vector<double> wf = wn_kernel(hp, r + "/Conv_filter/conv1d", 3, F, F), wg = wn_kernel(hp, r + "/Conv_gate/conv1d", 3, F, F);
-        std::vector<double> wcf = wn_kernel(hp, r + "/conv1d", 1, Kc, F), wcg = wn_kernel(hp, r + "/conv1d_1", 1, Kc, F);
+        Ref wf = wn_kernel(hp, r + "/Conv_filter/conv1d", 3, F, F), wg = wn_kernel(hp, r + "/Conv_gate/conv1d", 3, F, F);
+        Ref wcf = wn_kernel(hp, r + "/conv1d", 1, Kc, F), wcg = wn_kernel(hp, r + "/conv1d_1", 1, Kc, F);
         const int Kc16 = (Kc + 15) / 16 * 16;
         const int Kg = 3 * F + Kc16, Ng = 2 * F;
-        std::vector<double> W((size_t)Kg * Ng, 0.0), B(Ng);
+        PMat W((size_t)Kg * Ng), B(Ng);
         for (int k = 0; k < 3 * F; ++k)
           for (int ch = 0; ch < F; ++ch) {
             W[(size_t)k * Ng + 2 * ch] = wf[(size_t)k * F + ch];
@@ -396,23 +486,23 @@ int model_prepack(Model* m, cudaStream_t st) {
             W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch] = wcf[(size_t)l * F + ch];
             W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch + 1] = wcg[(size_t)l * F + ch];
           }
-        const float *bf = hp.p(r + "/Conv_filter/conv1d/bias"), *bg = hp.p(r + "/Conv_gate/conv1d/bias");
-        const float *bcf = hp.p(r + "/conv1d/bias"), *bcg = hp.p(r + "/conv1d_1/bias");
+        // bias of a gate column = conv bias + conditioning-conv bias: an `ext` slot of the folded vector (FOLD_SUM2)
+        Ref bfs = hp.ext(r + "/Conv_filter/conv1d/bias"), bgs = hp.ext(r + "/Conv_gate/conv1d/bias");
         for (int ch = 0; ch < F; ++ch) {
-          B[2 * ch] = (double)bf[ch] + bcf[ch];
-          B[2 * ch + 1] = (double)bg[ch] + bcg[ch];
+          B[2 * ch] = bfs[ch];
+          B[2 * ch + 1] = bgs[ch];
         }
         int ld;
-        fo.gate_w.push_back(store_matrix(b, W, Kg, Ng, bf16, &ld));
+        fo.gate_w.push_back(store_matrix(bw, b, W, Kg, Ng, bf16, &ld));
         if (!bf16) fo.w3[GEMM_GATE0 + n] = store_planes(b, W, Kg, Ng);
         fp.gate_ld = ld;
-        fo.gate_b.push_back(store_floats(b, B));
+        fo.gate_b.push_back(store_pvec(bw, B));
         // res | skip 1x1 (the last layer's residual output is dead in the reference graph: modules.py:170-176)
         const bool last = n == L - 1;
         const int Nr = last ? F : 2 * F;
-        std::vector<double> wr = wn_kernel(hp, r + "/conv1d_2", 1, F, F), ws = wn_kernel(hp, r + "/conv1d_3", 1, F, F);
-        const float *br = hp.p(r + "/conv1d_2/bias"), *bs = hp.p(r + "/conv1d_3/bias");
-        std::vector<double> W2((size_t)F * Nr), B2(Nr);
+        Ref wr = wn_kernel(hp, r + "/conv1d_2", 1, F, F), ws = wn_kernel(hp, r + "/conv1d_3", 1, F, F);
+        Ref br = hp.ref(r + "/conv1d_2/bias"), bs = hp.ref(r + "/conv1d_3/bias");
+        PMat W2((size_t)F * Nr), B2(Nr);
         for (int k = 0; k < F; ++k)
           for (int ch = 0; ch < F; ++ch) {
             if (!last) {
@@ -426,51 +516,47 @@ int model_prepack(Model* m, cudaStream_t st) {
           if (!last) { B2[ch] = br[ch]; B2[F + ch] = bs[ch]; }
           else B2[ch] = bs[ch];
         }
-        fo.rs_w.push_back(store_matrix(b, W2, F, Nr, bf16, &ld));
+        fo.rs_w.push_back(store_matrix(bw, b, W2, F, Nr, bf16, &ld));
         if (!bf16) fo.w3[GEMM_RS0 + n] = store_planes(b, W2, F, Nr);
         fp.rs_ld[n] = ld;
-        fo.rs_b.push_back(store_floats(b, B2));
+        fo.rs_b.push_back(store_pvec(bw, B2));
       }
       {
-        std::vector<double> w = wn_kernel(hp, wpre + "/Conv_final/conv1d", 1, F, F);
+        PMat w = pm_from(wn_kernel(hp, wpre + "/Conv_final/conv1d", 1, F, F), (size_t)F * F);
         int ld;
-        fo.final_w = store_matrix(b, w, F, F, bf16, &ld);
+        fo.final_w = store_matrix(bw, b, w, F, F, bf16, &ld);
         if (!bf16) fo.w3[GEMM_FINAL] = store_planes(b, w, F, F);
         fp.final_ld = ld;
-        const float* bb = hp.p(wpre + "/Conv_final/conv1d/bias");
-        fo.final_b = store_floats(b, std::vector<double>(bb, bb + F));
+        fo.final_b = store_pvec(bw, pm_from(hp.ref(wpre + "/Conv_final/conv1d/bias"), F));
       }
       {
         // ZeroConv1d (modules.py:51-56): (u.W + b) * exp(3 scale); exp folded into W and b.
         // Columns (2q, 2q+1) = (log_s, t) of the q-th transformed channel.  Additive coupling
         // (model.py:136-139,157-159) is expressed as log_s = 0, t = -net.
         const int out_ch = c.affine ? cx : nq;
-        const float* zk = hp.p(wpre + "/ZeroConv1d/conv1d/kernel");
-        const float* zb = hp.p(wpre + "/ZeroConv1d/conv1d/bias");
-        const float* zs = hp.p(wpre + "/ZeroConv1d/scale");
+        Ref zk = hp.ref(wpre + "/ZeroConv1d/conv1d/kernel");   // exp(3 scale) already folded in (FOLD_ZERO)
+        Ref zb = hp.ref(wpre + "/ZeroConv1d/conv1d/bias");
         const int Nz = 2 * nq;
-        std::vector<double> W((size_t)F * Nz, 0.0), B(Nz, 0.0);
+        PMat W((size_t)F * Nz), B(Nz);
         for (int p2 = 0; p2 < nq; ++p2) {   // column pair p2 <- logical transformed channel q = qperm[p2]
           const int q = qperm[p2];
           if (c.affine) {
-            const double e0 = exp(3.0 * (double)zs[q]), e1 = exp(3.0 * (double)zs[nq + q]);
             for (int k = 0; k < F; ++k) {
-              W[(size_t)k * Nz + 2 * p2] = zk[(size_t)k * out_ch + q] * e0;
-              W[(size_t)k * Nz + 2 * p2 + 1] = zk[(size_t)k * out_ch + nq + q] * e1;
+              W[(size_t)k * Nz + 2 * p2] = zk[(size_t)k * out_ch + q];
+              W[(size_t)k * Nz + 2 * p2 + 1] = zk[(size_t)k * out_ch + nq + q];
             }
-            B[2 * p2] = zb[q] * e0;
-            B[2 * p2 + 1] = zb[nq + q] * e1;
+            B[2 * p2] = zb[q];
+            B[2 * p2 + 1] = zb[nq + q];
           } else {
-            const double e0 = exp(3.0 * (double)zs[q]);
-            for (int k = 0; k < F; ++k) W[(size_t)k * Nz + 2 * p2 + 1] = -(double)zk[(size_t)k * out_ch + q] * e0;
-            B[2 * p2 + 1] = -(double)zb[q] * e0;
+            for (int k = 0; k < F; ++k) W[(size_t)k * Nz + 2 * p2 + 1] = -zk[(size_t)k * out_ch + q];
+            B[2 * p2 + 1] = -zb[q];
           }
         }
         int ld;
-        fo.zero_w = store_matrix(b, W, F, Nz, bf16, &ld);
+        fo.zero_w = store_matrix(bw, b, W, F, Nz, bf16, &ld);
         if (!bf16) fo.w3[GEMM_ZERO] = store_planes(b, W, F, Nz);
         fp.zero_ld = ld;
-        fo.zero_b = store_floats(b, B, (Nz + 15) / 16 * 16);
+        fo.zero_b = store_pvec(bw, B, (Nz + 15) / 16 * 16);
       }
       m->flows.push_back(fp);
       offs.push_back(fo);
@@ -487,10 +573,18 @@ int model_prepack(Model* m, cudaStream_t st) {
   reinterpret_cast<double*>(b.buf.data() + scal)[0] = an_logdet;
   if (m->pack) FWN_CUDA(cudaFree(m->pack));
   m->pack = nullptr;
-  FWN_CUDA(cudaMalloc(&m->pack, b.buf.size()));
-  m->pack_bytes = b.buf.size();
-  FWN_CUDA(cudaMemcpy(m->pack, b.buf.data(), b.buf.size(), cudaMemcpyHostToDevice));
-  char* base = m->pack;
+  // device layout: [fp32 region (wall_floats) | everything else]
+  const size_t wall_bytes = (bw.v.size() * 4 + 255) & ~size_t(255);
+  FWN_CUDA(cudaMalloc(&m->pack, wall_bytes + b.buf.size()));
+  m->pack_bytes = wall_bytes + b.buf.size();
+  m->wall_floats = (int64_t)bw.v.size();
+  FWN_CUDA(cudaMemcpy(m->pack, bw.v.data(), bw.v.size() * 4, cudaMemcpyHostToDevice));
+  FWN_CUDA(cudaMemcpy(m->pack + wall_bytes, b.buf.data(), b.buf.size(), cudaMemcpyHostToDevice));
+  if (m->keep_map) m->host_wmap = bw.code; else m->host_wmap.clear();
+  struct BasePtr {  // resolves a tagged staging offset to its device address
+    char* wall; char* rest;
+    char* operator+(size_t off) const { return (off & IN_WALL) ? wall + (off & ~IN_WALL) * 4 : rest + off; }
+  } base{m->pack, m->pack + wall_bytes};
   m->d_an_logdet = reinterpret_cast<double*>(base + scal);
   for (int i = 0; i < c.n_upsample; ++i) {
     m->up_w[i] = reinterpret_cast<float*>(base + up_w[i]);
@@ -523,7 +617,7 @@ int model_prepack(Model* m, cudaStream_t st) {
   model_drop_graphs(m);
   m->packed = true;
   m->plan_B = m->plan_T = -1;  // tensor maps (tcgen05 engine) must be rebuilt
-  return 0;
+  return train_after_prepack(m);     // training enabled: rebuild the state that points into the pack buffer
 }
 
 // ---------------------------------------------------------------- optional CUDA-event profiling
@@ -673,7 +767,7 @@ __global__ void finish_forward_kernel(const double* sums, const double* an_logde
   if (logdet_out) *logdet_out = (float)(*an_logdet - sums[0] / n);
 }
 
-static int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st) {
+int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st) {
   const fwn_config& c = m->cfg;
   const bool bf16 = c.precision == FWN_MIXED_BF16;
   int Tm = T / m->hop;
@@ -699,6 +793,12 @@ static int run_upsample(const Model* m, const Workspace& w, const float* c_in, i
 }
 
 // One coupling WaveNet + the in-place flow update of X (ActNorm + AffineCoupling [+ change_order absorbed]).
+int finish_forward(const double* sums, const double* an_logdet, float* logp_out, float* logdet_out, double n, cudaStream_t st) {
+  finish_forward_kernel<<<1, 1, 0, st>>>(sums, an_logdet, logp_out, logdet_out, n);
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
 static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, int B, int Ti, bool reverse, cudaStream_t st) {
   const fwn_config& c = m->cfg;
   const int F = c.filter_size, L = c.n_layer;

@@ -57,6 +57,17 @@ struct Workspace {
 
 
 struct TcPlan;  // tensor maps of the tcgen05 engine (gemm_tc.cu)
+struct TrainState;  // training-step state (train.cu)
+
+// How the folded parameter vector What (raw layout + `ext` slots) derives from the raw variables.  The packed GEMM operands are pure
+// signed gathers of What (model_prepack builds the gather map), so the same two steps -- fold, gather -- run on the host at
+// fwn_prepack and on the device after every optimizer step, and their transposes carry the gradients back (train.cu).
+enum FoldKind {
+  FOLD_WN = 0,    // weight norm (convolutional.py:73-83): What[a + k N + o] = v[k,o] g[o] rsqrt(max(sum_k v[k,o]^2, 1e-12));  a = kernel, b = g
+  FOLD_ZERO = 1,  // ZeroConv1d (modules.py:51-56): What[a + k N + o] = W[k,o] e[o], What[b + o] = bias[o] e[o], e = exp(3 scale[o]); c = scale
+  FOLD_SUM2 = 2   // What[raw_floats + d + j] = raw[a + j] + raw[b + j]   (conv bias + conditioning-conv bias of one gate column)
+};
+struct FoldDesc { int kind; int64_t a, b, c, d; int K, N; };
 
 struct Model {
   fwn_config cfg;
@@ -65,6 +76,13 @@ struct Model {
   std::unordered_map<std::string, int> index;
   float* raw = nullptr;
   int64_t raw_floats = 0;
+  std::vector<FoldDesc> folds;
+  std::unordered_map<std::string, int64_t> ext_of;  // first bias name of a FOLD_SUM2 -> its ext slot
+  int64_t ext_floats = 0;
+  int64_t wall_floats = 0;          // leading fp32 region of `pack`: every packed fp32 GEMM operand and bias vector, contiguous
+  bool keep_map = false;            // fwn_train_enable: keep the gather map of that region
+  std::vector<int32_t> host_wmap;   // [wall_floats] What index | sign << 30, -1 = constant
+  TrainState* train = nullptr;
   bool packed = false, rev_ok = false;
   char* pack = nullptr;
   size_t pack_bytes = 0;

@@ -1,0 +1,82 @@
+// Training-step internals (train.cu, train_kernels.cu).  Reference: train.py:15-32,56-81, utils.py:34-60.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "model.h"
+
+namespace fwn {
+
+struct FoldWork { int desc; int col0; };
+
+// one fp32 operand (or a K range of one) -> bf16x3 planes:  dst[p][n][k0 + k] = split_p(src[k sk + n sn])
+struct PlaneDesc {
+  const float* src;
+  int64_t sk, sn;
+  int K, N;
+  __nv_bfloat16* dst;
+  int Kpad, Npad, k0;
+};
+struct PlaneWork { int desc, kt, nt; };
+
+struct ActnormDesc {
+  const float *raw_b, *raw_logs;
+  float *an_b, *an_s, *an_is;
+  const int* off2log;
+  int Cx;
+};
+
+struct WgradArgs {
+  Seg seg[4];
+  int nseg;
+  const float* dY0; int64_t ld0; int n0cols;   // dY columns [0, n0cols) come from dY0, [n0cols, N) from dY1
+  const float* dY1; int64_t ld1;
+  int N;
+  float* dW; int64_t ldw;                      // [Ktot, ldw] fp32, accumulated with atomics
+  int B, Ti;
+  int slabs_per_utt;                           // set by wgrad()
+};
+
+// ---- train_kernels.cu
+int fold_forward(const float* raw, float* what, const FoldDesc* descs, const FoldWork* work, int nwork, int64_t raw_floats, cudaStream_t st);
+int fold_backward(const float* raw, float* G, const FoldDesc* descs, const FoldWork* work, int nwork, int64_t raw_floats, cudaStream_t st);
+int gather_pack(const float* what, const int32_t* map, float* P, int64_t n, cudaStream_t st);
+int scatter_grad(const float* gP, const int32_t* map, float* G, int64_t n, cudaStream_t st);
+int make_planes(const PlaneDesc* descs, const PlaneWork* work, int nwork, cudaStream_t st);
+int actnorm_pack(const ActnormDesc* descs, int nflows, double* an_logdet, cudaStream_t st);
+int wgrad(const WgradArgs& a, cudaStream_t st);
+int colsum(const float* dY0, int64_t ld0, int n0cols, const float* dY1, int64_t ld1, int N, int64_t rows, float* out, cudaStream_t st);
+int logp_bwd(const float* z, float* dX, int64_t n, cudaStream_t st);
+int affine_bwd(float* dX, const float* Xpost, const float* net, int64_t ldn, float* dNet, int64_t rows, int Cx, int nq, const int* b_off,
+               double n_total, cudaStream_t st);
+int actnorm_bwd(float* dX, const float* da0, int ld_a0, const float* xpre, const float* an_b, const float* an_s, const int* off2log,
+                int64_t rows, int Cx, int nq, float* g_b, float* g_logs, cudaStream_t st);
+int front_pack_f32(const float* X, int Cx, int nq, int kq, const int* off2log, const float* an_b, const float* an_s, float* A0, int64_t rows,
+                   cudaStream_t st);
+int upsample_bwd_stage(const float* dout0, const float* dout1, const float* out0, const float* out1, bool split, const float* in,
+                       const float* w, float* dw_scratch, float* din, int B, int Tm, int mels, int s, cudaStream_t st);
+int upsample_wn_bwd(const float* v, const float* g, const float* dw, int s, float* gv, float* gg, cudaStream_t st);
+int grad_global_norm(const float* g, int64_t n, double* scratch, float* norm_out, cudaStream_t st);
+int adam_update(float* p, float* m, float* v, const float* g, const float* norm, float clip, float lr, float b1, float b2, float eps,
+                int64_t step, int64_t n, cudaStream_t st);
+
+// ---- gemm_tc3.cu
+bool tc3_supported(const GemmArgs& g);
+int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, cudaStream_t st);
+
+// ---- model.cu helpers shared with the training pass
+int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st);
+int finish_forward(const double* sums, const double* an_logdet, float* logp_out, float* logdet_out, double n, cudaStream_t st);
+
+// ---- train.cu
+int train_enable(Model* m, cudaStream_t st);
+int train_after_prepack(Model* m);
+void train_free(Model* m);
+int64_t train_workspace_bytes(const Model* m, int B, int T);
+int64_t train_grad_floats(const Model* m);
+int train_loss_and_grads(Model* m, const float* x, const float* c, const int32_t* g, int B, int T, float* logp_out, float* logdet_out,
+                         float* grads, int64_t grad_floats, void* ws, int64_t ws_bytes, cudaStream_t st);
+int train_grad_norm(Model* m, const float* grads, float* norm_out, cudaStream_t st);
+int train_apply(Model* m, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm, int64_t step, cudaStream_t st);
+int train_repack(Model* m, cudaStream_t st);
+
+}  // namespace fwn
