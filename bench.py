@@ -34,6 +34,11 @@ WORKLOADS = {
     "c4s": ("hparams", "reverse", 1, 5168, "bfloat16", "C4: hparams inverse synthesis, ONE 60 s utterance (T=1323008) sharded by time chunk across the GPUs, "
             "15616-sample receptive-field halos exchanged with NCCL send/recv, mixed precision"),
 }
+TRAIN_WORKLOADS = {
+    # name: (preset, B per GPU, n_frames, gin_channels, n_speakers, description)
+    "c5": ("hparams", 8, 25, 16, 7, "C5: hparams training step (forward + backward + tower-average + clip + Adam + re-pack), 8 utterances x 6400 samples "
+           "per GPU (hparams.py:28,36), fp32 variables/activations, GEMMs on tcgen05 via 3-way bf16 split (fp32-accurate), CUDA-core wgrad"),
+}
 MFLOP_PER_SAMPLE = {"hparams": 17.31174, "hparams8000": 15.448592}  # SURVEY 8d algorithmic 2*MAC per audio sample
 
 
@@ -109,15 +114,174 @@ def cpu_sample_shape(preset, B, n_frames):
     return 1, min(n_frames, 87)                # 1 x 1.01 s of 22.05 kHz audio
 
 
+def oracle_train_step(hp_kw, B, n_frames, seed=1234):
+    """loss + gradients of one tower on the CPU restatement (the `port` baseline of the training step)."""
+    import torch
+    from oracle import flowavenet_oracle as O
+    from oracle import flowavenet_train_oracle as TO
+    hp = O.HP(**hp_kw)
+    params = O.synthetic_params(hp, seed)
+    x, c = O.synthetic_inputs(hp, B, n_frames, seed + 1, "x")
+    torch.set_num_threads(os.cpu_count() or 1)
+    TO.loss_and_grads(params, hp, x, c, torch.float32)  # warm-up
+    best = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        TO.loss_and_grads(params, hp, x, c, torch.float32)
+        best = min(best, time.perf_counter() - t0)
+    return B * n_frames * hp.hop, best, torch.get_num_threads()
+
+
+def main_train(args):
+    """C5: one training step per `step` (train.py:236), data-parallel towers = processes, gradients averaged with one NCCL all-reduce."""
+    preset, B, n_frames, gin, nspk, desc = TRAIN_WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "training audio samples/sec"
+    import tf_flowavenet_b200 as P
+    hp_ref = getattr(P, preset)
+    hop = int(np.prod(hp_ref.upsample_scales))
+    T = n_frames * hop
+    hp_kw = dict(n_block=hp_ref.n_block, upsample_scales=tuple(hp_ref.upsample_scales))
+    config = {"workload": desc, "preset": preset, "direction": "train", "utterances_per_gpu": B, "samples_per_utterance": T,
+              "global_batch": B * max(world, args.gpus), "gin_channels": gin, "n_speakers": nspk, "sample_rate": hp_ref.sample_rate,
+              "parallelism": "dp%d: one tower per GPU, all-reduce(avg) of the flat fp32 gradient (181 M floats)" % max(world, args.gpus),
+              "l2_policy": "per-step working set (tape ~3 GB + 2.2 GB of weights and operands) >> 126 MB L2; no explicit flush needed"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        samples, secs, thr = oracle_train_step(hp_kw, 1, n_frames)
+        val = samples / secs
+        sample = "1 utterance x %d frames (%d samples): loss + autograd gradients of the same model, fp32, best of 2 after 1 warm-up" % (n_frames, samples)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": "samples/s", "cores": thr, "kind": "port", "sample": sample,
+                                           "note": "CPU restatement (PyTorch-CPU autograd) of the reference training graph; optimizer update not included"},
+                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tf_flowavenet_b200.synthetic import synthetic_inputs, synthetic_params
+    from tf_flowavenet_b200.train import Trainer
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    net = P.FloWaveNet(P.HParams(**{**hp_ref.values(), "dtype": "float32", "gin_channels": gin, "n_speakers": nspk}), variables=P.VariableStore())
+    net.load_variables(synthetic_params(net.variable_shapes(), seed=1234))   # same variables on every tower
+    x_np, c_np = synthetic_inputs(hop, 80, B, n_frames, 1234 + 5 + rank, "x")  # each tower draws its own batch (dataset.py:34-38)
+    g_np = np.random.default_rng(77 + rank).integers(0, nspk, size=(B,)).astype(np.int32)
+    x_pin, c_pin, g_pin = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(c_np).pin_memory(), torch.from_numpy(g_np).pin_memory()
+    x_dev, c_dev, g_dev = x_pin.cuda(), c_pin.cuda(), g_pin.cuda()
+    tr = Trainer(net)
+    tr.train_step(x_dev, c_dev, g_dev, init=True)  # ActNorm DDI step (train.py:221,229)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    phase = [0.0, 0.0, 0.0]
+
+    def step_dev(timed=False):
+        if timed:
+            ev[0].record()
+        tr.loss_and_grads(x_dev, c_dev, g_dev)
+        if timed:
+            ev[1].record()
+        tr.average_gradients()
+        if timed:
+            ev[2].record()
+        tr.apply_gradients()
+        if timed:
+            ev[3].record()
+            ev[3].synchronize()
+            for i in range(3):
+                phase[i] += ev[i].elapsed_time(ev[i + 1])
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = net.last_launches() * args.steps
+    for _ in range(args.steps):   # same steps again with CUDA events between the phases
+        step_dev(timed=True)
+    barrier()
+    # end to end: pinned host batch -> device, step, loss back to the host, every step
+    def step_e2e():
+        xd, cd, gd = x_pin.cuda(non_blocking=True), c_pin.cuda(non_blocking=True), g_pin.cuda(non_blocking=True)
+        info = tr.train_step(xd, cd, gd)
+        return float(info["loss"])
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    samples_per_step = B * T * world
+    value = samples_per_step * args.steps / (ms * 1e-3)
+    flop_step = 3.0 * MFLOP_PER_SAMPLE[preset] * 1e6 * B * T   # forward + dgrad + wgrad, per GPU
+    ach = flop_step / (phase[0] / args.steps * 1e-3) / 1e12
+    roof = {"kernel": "forward+backward of one tower (tc3_gemm_kernel: fwd + dgrad GEMMs; wgrad_kernel: CUDA-core wgrad)", "bound": "tensor",
+            "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+            "peak_source": "%s bf16_tflops_sustained; fp32-accurate GEMMs spend 6 bf16 MMA terms per product, so the attainable fraction "
+                           "of this peak is 1/6 for the tensor-core GEMMs" % pk["src"],
+            "traffic": None, "algorithmic_flop_per_step_per_gpu": flop_step,
+            "phases_ms_per_step": {"loss_and_grads": phase[0] / args.steps, "allreduce_avg": phase[1] / args.steps,
+                                   "clip_adam_repack": phase[2] / args.steps}}
+    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "roofline": roof, "clocks": clk,
+            "e2e": {"value": samples_per_step * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": x_pin.numel() * 4 + c_pin.numel() * 4 + g_pin.numel() * 4, "d2h_bytes_per_step": 4,
+                    "api": "Trainer.train_step -> fwn_loss_and_grads + all_reduce + fwn_apply_gradients", "last_loss": loss},
+            "gpu_launches": int(launches)}
+    if not args.no_cpu_baseline and world == 1:
+        samples, secs, thr = oracle_train_step(hp_kw, 1, n_frames)
+        line["cpu_baseline"] = {"value": samples / secs, "unit": "samples/s", "cores": thr, "kind": "port",
+                                "sample": "1 utterance x %d frames (%d samples): loss + autograd gradients, fp32, best of 2 after 1 warm-up" % (n_frames, samples),
+                                "note": "CPU restatement (PyTorch-CPU autograd) of the reference training graph; baseline only"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload in TRAIN_WORKLOADS:
+        return main_train(args)
     preset, direction, B, n_frames, dtype, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -10,6 +10,8 @@
 // mirror the forward cA / cB layout, so squeeze and change_order need no backward kernels either.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "train.h"
@@ -189,6 +191,7 @@ int train_repack(Model* m, cudaStream_t st) {
   TrainState* t = m->train;
   FWN_CHECK(t, "training not enabled: call fwn_train_enable first");
   const fwn_config& c = m->cfg;
+  m->launches += 4 + 1 * c.n_upsample;
   if (fold_forward(m->raw, t->what, t->d_folds, t->d_fwork, t->n_fwork, m->raw_floats, st)) return 1;
   if (gather_pack(t->what, t->wmap, reinterpret_cast<float*>(m->pack), m->wall_floats, st)) return 1;
   if (make_planes(t->d_pdesc, t->d_pwork, t->n_pwork, st)) return 1;
@@ -271,6 +274,15 @@ static int bw_gemm(Model* m, const GemmArgs& g, EpiKind kind, const W3& w3, cuda
   m->launches++;
   FWN_CHECK(w3.p && tc3_supported(g), "internal: backward GEMM operand not supported by the split engine");
   return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, st);
+}
+// FWN_WGRAD = tc3 (default) | simt
+static bool wgrad_on_tensor_cores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_WGRAD");
+    v = (e && !strcmp(e, "simt")) ? 0 : 1;
+  }
+  return v == 1;
 }
 static inline int shift_of(const fwn_config& c, int k, int d) { return c.causal ? (k - 2) * d : (k - 1) * d; }
 
@@ -361,7 +373,11 @@ static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const T
     a.dY0 = y0; a.ld0 = ld0; a.n0cols = n0; a.dY1 = y1; a.ld1 = ld1; a.N = N;
     a.dW = gw(m, P); a.ldw = ldw; a.B = B; a.Ti = Ti;
     m->launches += 2;
-    if (wgrad(a, st)) return 1;
+    if (wgrad_on_tensor_cores() && wgrad_tc3_supported(a)) {
+      if (wgrad_tc3(a, st)) return 1;
+    } else if (wgrad(a, st)) {
+      return 1;
+    }
     return colsum(y0, ld0, n0, y1, ld1, N, rows, gw(m, bias_slot), st);
   };
 
@@ -526,6 +542,7 @@ int train_apply(Model* m, const float* grads, float lr, float beta1, float beta2
   FWN_CHECK(m && m->train, "training not enabled");
   FWN_CHECK(step >= 1, "Adam step counter starts at 1");
   TrainState* t = m->train;
+  m->launches += 3;
   if (grad_global_norm(grads, m->raw_floats, t->scratch, t->norm, st)) return 1;
   if (adam_update(m->raw, t->adam_m, t->adam_v, grads, t->norm, clip_norm, lr, beta1, beta2, eps, step, m->raw_floats, st)) return 1;
   return train_repack(m, st);

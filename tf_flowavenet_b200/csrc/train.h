@@ -59,6 +59,10 @@ int grad_global_norm(const float* g, int64_t n, double* scratch, float* norm_out
 int adam_update(float* p, float* m, float* v, const float* g, const float* norm, float clip, float lr, float b1, float b2, float eps,
                 int64_t step, int64_t n, cudaStream_t st);
 
+// ---- wgrad_tc3.cu (tensor-core wgrad, fp32-accurate)
+bool wgrad_tc3_supported(const WgradArgs& a);
+int wgrad_tc3(const WgradArgs& a, cudaStream_t st);
+
 // ---- gemm_tc3.cu
 bool tc3_supported(const GemmArgs& g);
 int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, cudaStream_t st);
