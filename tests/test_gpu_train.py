@@ -28,18 +28,20 @@ def check_grads(got, ref, tol=5e-4):
     assert worst[1] < tol, worst
 
 
+@pytest.mark.parametrize("terms", [3, 6])
 @pytest.mark.parametrize("case", GRAD_CASES)
-def test_gradients_match_oracle(case):
+def test_gradients_match_oracle(case, terms):
+    """terms = bf16 products per fp32 product on the tensor cores: 3 (training default, ~2^-16 per product) and 6 (fp32 accuracy)."""
     import tf_flowavenet_b200.train as T
     hp, params, fx = load(case)
     net = make_model(hp, params)
-    tr = T.Trainer(net)
+    tr = T.Trainer(net, split_terms=terms)
     x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
     log_p, logdet = tr.loss_and_grads(x, c)
     np.testing.assert_allclose(float(log_p), float(fx["log_p"]), rtol=1e-4)
     np.testing.assert_allclose(float(logdet), float(fx["logdet"]), rtol=1e-4, atol=1e-6)
     _, _, _, ref = TO.loss_and_grads(params, hp, torch.from_numpy(fx["x"]), torch.from_numpy(fx["c"]))
-    check_grads(tr.gradients(), ref)
+    check_grads(tr.gradients(), ref, tol=5e-4 if terms == 3 else 2e-4)
     # deterministic up to atomics: a second call agrees to fp32 rounding
     g1 = tr.grads.clone()
     tr.loss_and_grads(x, c)

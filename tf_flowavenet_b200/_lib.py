@@ -47,6 +47,7 @@ SIGNATURES = {
     "fwn_loss_and_grads": (_i, [_p, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _l, _p, _l, _p]),
     "fwn_grad_global_norm": (_i, [_p, _fp, _fp, _p]),
     "fwn_apply_gradients": (_i, [_p, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _l, _p]),
+    "fwn_set_split_terms": (_i, [_p, _i, _i]),
     "fwn_repack": (_i, [_p, _p]),
     "fwn_last_launches": (_l, [_p]),
     "fwn_profile_enable": (_i, [_p, _i]),

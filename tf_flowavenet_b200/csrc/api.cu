@@ -184,6 +184,14 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
   FWN_CHECK(h && grads, "null argument");
   return train_apply(h->m, grads, lr, beta1, beta2, eps, clip_norm, step, S(stream));
 }
+int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms) {
+  FWN_CHECK(h, "null handle");
+  FWN_CHECK((inference_terms == 3 || inference_terms == 6) && (training_terms == 3 || training_terms == 6), "split terms must be 3 or 6");
+  h->m->terms_infer = h->m->cur_terms = inference_terms;
+  h->m->terms_train = training_terms;
+  model_drop_graphs(h->m);   // captured launches carry the old setting
+  return 0;
+}
 int fwn_repack(fwn_handle h, void* stream) {
   FWN_CHECK(h, "null handle");
   return train_repack(h->m, S(stream));

@@ -15,7 +15,7 @@ int tc_prepare(Model* m, const Workspace& w, int B, int T, cudaStream_t st);
 int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPack& fp, cudaStream_t st);
 void tc_free(Model* m);
 bool tc3_supported(const GemmArgs& g);
-int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, cudaStream_t st);
+int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, int nterms, cudaStream_t st);
 
 // FWN_FP32_ENGINE = tc3 (default) | simt
 static bool fp32_split_engine() {
@@ -36,7 +36,7 @@ int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowP
   m->launches++;
   if (m->cfg.precision == FWN_FP32) {
     const W3& w3 = fp.w3[gemm_id];
-    if (w3.p && fp32_split_engine() && tc3_supported(g)) return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, st);
+    if (w3.p && fp32_split_engine() && tc3_supported(g)) return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, m->cur_terms, st);
     return simt_gemm(g, kind, st);
   }
   return tc_run(m, g, kind, gemm_id, fp, st);

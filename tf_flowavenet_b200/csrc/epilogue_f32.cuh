@@ -12,19 +12,42 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + exp
 // Called with 4 consecutive columns (col % 4 == 0) of one row.
 template <int EPI>
 struct Epilogue {
-  __device__ static __forceinline__ void apply(const GemmArgs& g, int64_t row, int t, int col, const float acc[4], double& ls_sum) {
+  // LINEAR accumulates in place (in0 == out0 is allowed), so the compiler must keep every load of in0 behind the preceding store:
+  // callers that walk many columns per row fetch the addends of a whole batch first (prefetch), then call apply with `pre`.
+  __device__ static __forceinline__ void prefetch(const GemmArgs& g, int64_t row, int col, float pre[4]) {
+    const EpiArgs& e = g.e;
+    pre[0] = pre[1] = pre[2] = pre[3] = 0.f;
+    if (EPI != EPI_LINEAR || !e.in0) return;
+    const float* a0 = reinterpret_cast<const float*>(e.in0) + row * e.ld + col;
+    if (col + 3 < g.N && (e.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a0) & 15) == 0) {
+      const float4 v = *reinterpret_cast<const float4*>(a0);
+      pre[0] = v.x; pre[1] = v.y; pre[2] = v.z; pre[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (col + j < g.N) pre[j] = a0[j];
+    }
+  }
+  __device__ static __forceinline__ void apply(const GemmArgs& g, int64_t row, int t, int col, const float acc[4], double& ls_sum,
+                                               const float* pre = nullptr) {
     const EpiArgs& e = g.e;
     if (EPI == EPI_PLAIN) {
       float* y = reinterpret_cast<float*>(e.out0) + row * e.ld;
+      float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int n = col + j;
+        const int n = col + j;
+        v[j] = acc[j];
         if (n < g.N) {
-          float v = acc[j];
-          if (e.colscale) v *= __ldg(e.colscale + n);
-          v += __ldg(e.bias + n);
-          y[n] = e.relu ? fmaxf(v, 0.f) : v;
+          if (e.colscale) v[j] *= __ldg(e.colscale + n);
+          v[j] += __ldg(e.bias + n);
+          if (e.relu) v[j] = fmaxf(v[j], 0.f);
         }
+      }
+      if (col + 3 < g.N && (e.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(y + col) & 15) == 0) {
+        *reinterpret_cast<float4*>(y + col) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < g.N) y[col + j] = v[j];
       }
     } else if (EPI == EPI_GATE) {
       // columns (2c, 2c+1) = (filter_c, gate_c)  -> o[row, c] = tanh(f) * sigmoid(g)   (modules.py:124)
@@ -88,19 +111,26 @@ struct Epilogue {
       }
     } else if (EPI == EPI_LINEAR) {
       float* y = reinterpret_cast<float*>(e.out0) + row * e.ld;
-      const float* a0 = e.in0 ? reinterpret_cast<const float*>(e.in0) + row * e.ld : nullptr;
+      const float* a0 = (e.in0 && !pre) ? reinterpret_cast<const float*>(e.in0) + row * e.ld : nullptr;
       const float* mk = e.in1 ? reinterpret_cast<const float*>(e.in1) + row * e.ld : nullptr;
+      float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = col + j;
+        v[j] = acc[j];
         if (n < g.N) {
-          float v = acc[j];
-          if (e.bias) v += __ldg(e.bias + n);
-          if (a0) v += a0[n];
-          v *= e.alpha;
-          if (mk && !(mk[n] > 0.f)) v = 0.f;
-          y[n] = v;
+          if (e.bias) v[j] += __ldg(e.bias + n);
+          if (pre) v[j] += pre[j];
+          else if (a0) v[j] += a0[n];
+          v[j] *= e.alpha;
+          if (mk && !(__ldg(mk + n) > 0.f)) v[j] = 0.f;
         }
+      }
+      if (col + 3 < g.N && (e.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(y + col) & 15) == 0) {
+        *reinterpret_cast<float4*>(y + col) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < g.N) y[col + j] = v[j];
       }
     } else if (EPI == EPI_GATE_BWD) {
       // o = tanh(f) sigmoid(g):  df = do sigmoid(g) (1 - tanh^2 f),  dg = do tanh(f) sigmoid(g) (1 - sigmoid(g))

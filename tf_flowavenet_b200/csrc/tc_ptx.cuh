@@ -257,6 +257,16 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
 }
 
 
+// fp32 pair -> three packed bf16 pairs with x = a1 + a2 + a3 (round-to-nearest pieces: |a2| <= 2^-9 |x|, |a3| <= 2^-18 |x|; unbiased).
+// Truncating instead of rounding would be cheaper but biases every piece towards zero, and the bias survives the cancellation in
+// gradient sums (measured: 5% error on a weight gradient with 3 product terms).
+__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  p1 = pack_bf16(x0, x1);
+  const float r0 = x0 - __uint_as_float(p1 << 16), r1 = x1 - __uint_as_float(p1 & 0xFFFF0000u);
+  p2 = pack_bf16(r0, r1);
+  p3 = pack_bf16(r0 - __uint_as_float(p2 << 16), r1 - __uint_as_float(p2 & 0xFFFF0000u));
+}
+
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

@@ -273,7 +273,7 @@ int64_t train_grad_floats(const Model* m) { return m->raw_floats + m->ext_floats
 static int bw_gemm(Model* m, const GemmArgs& g, EpiKind kind, const W3& w3, cudaStream_t st) {
   m->launches++;
   FWN_CHECK(w3.p && tc3_supported(g), "internal: backward GEMM operand not supported by the split engine");
-  return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, st);
+  return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, m->cur_terms, st);
 }
 // FWN_WGRAD = tc3 (default) | simt
 static bool wgrad_on_tensor_cores() {
@@ -374,7 +374,7 @@ static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const T
     a.dW = gw(m, P); a.ldw = ldw; a.B = B; a.Ti = Ti;
     m->launches += 2;
     if (wgrad_on_tensor_cores() && wgrad_tc3_supported(a)) {
-      if (wgrad_tc3(a, st)) return 1;
+      if (wgrad_tc3(a, m->cur_terms, st)) return 1;
     } else if (wgrad(a, st)) {
       return 1;
     }
@@ -474,6 +474,8 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   const fwn_config& c = m->cfg;
   TrainState* t = m->train;
   m->launches = 0;
+  struct TermsGuard { Model* m; ~TermsGuard() { m->cur_terms = m->terms_infer; } } terms_guard{m};
+  m->cur_terms = m->terms_train;
   const size_t BT = (size_t)B * T;
   const int H = c.num_mels / 2;
   FWN_CUDA(cudaMemcpyAsync(w.X, x, BT * 4, cudaMemcpyDeviceToDevice, st));

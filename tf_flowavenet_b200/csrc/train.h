@@ -61,11 +61,11 @@ int adam_update(float* p, float* m, float* v, const float* g, const float* norm,
 
 // ---- wgrad_tc3.cu (tensor-core wgrad, fp32-accurate)
 bool wgrad_tc3_supported(const WgradArgs& a);
-int wgrad_tc3(const WgradArgs& a, cudaStream_t st);
+int wgrad_tc3(const WgradArgs& a, int nterms, cudaStream_t st);
 
 // ---- gemm_tc3.cu
 bool tc3_supported(const GemmArgs& g);
-int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, cudaStream_t st);
+int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad, int nterms, cudaStream_t st);
 
 // ---- model.cu helpers shared with the training pass
 int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st);

@@ -2,7 +2,7 @@
 //   dW[koff + k, n] += sum_{b,t} A[b, t + shift, k] * dY[b, t, n]
 // The reduction runs over time, so both operands are needed "transposed" (reduction index contiguous).  TMA brings fp32 tiles
 // [64 time steps x 128 channels] of A and dY into shared memory; eight converter warps read them COLUMN-wise (one channel per
-// thread, conflict-free), split each value exactly into three bf16 pieces (truncation: 8 + 8 + 8 significand bits) and write the
+// thread, conflict-free), split each value into three bf16 pieces (round-to-nearest, unbiased) and write the
 // K-major, 128B-swizzled operand tiles [128 channels x 64 time steps] x 3 planes that tcgen05.mma consumes.  Six MMA groups per
 // chunk (a1y1, a1y2, a2y1, a2y2, a1y3, a3y1).  A CTA owns one [128 k x 128 n] tile of dW and a slab of whole 64-step chunks of
 // one utterance; partial tiles are combined with fp32 atomics (coalesced through a shared-memory transpose).
@@ -27,7 +27,7 @@ constexpr int BOX_BYTES = MC * 128;            // one TMA box [64 rows x 32 floa
 constexpr int STG_A = 4 * BOX_BYTES, STG_Y = 4 * BOX_BYTES, STAGE_BYTES = STG_A + STG_Y;   // 64 KB
 constexpr int NST = 2;
 constexpr int PL_A = 3 * A_BYTES, PL_Y = 3 * A_BYTES;                                      // 48 KB each
-constexpr int CONV_WARPS = 8;
+constexpr int CONV_WARPS = 16;                 // thread = (channel, half of the 64 time steps)
 constexpr int THREADS = 64 + CONV_WARPS * 32 + 128;
 constexpr size_t SMEM = 1024 + (size_t)NST * STAGE_BYTES + PL_A + PL_Y + 256;
 constexpr int TSTRIDE = 129;                   // fp32 transpose buffer row pitch (floats)
@@ -40,7 +40,8 @@ struct alignas(64) Wg3Args {
   int nseg, n0cols, N;
   float* dW;
   int64_t ldw;
-  int B, Ti, chunks_per_utt, slabs_per_utt;
+  int B, Ti, chunks_per_utt, slabs;   // slab = contiguous range of (utterance, chunk) pairs
+  int nterms;   // 6 or 3, as in gemm_tc3.cu
 };
 
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_constant__ Wg3Args a) {
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
   int kt = blockIdx.x, sidx = 0;
   while (sidx < a.nseg - 1 && kt >= a.ktiles[sidx]) { kt -= a.ktiles[sidx]; ++sidx; }
   const int k0 = kt * 128, n0 = blockIdx.y * BNW;
-  const int ub = blockIdx.z / a.slabs_per_utt, sl = blockIdx.z - ub * a.slabs_per_utt;
-  const int c_begin = (int)((int64_t)a.chunks_per_utt * sl / a.slabs_per_utt), c_end = (int)((int64_t)a.chunks_per_utt * (sl + 1) / a.slabs_per_utt);
+  const int64_t total_chunks = (int64_t)a.B * a.chunks_per_utt;
+  const int c_begin = (int)(total_chunks * blockIdx.z / a.slabs), c_end = (int)(total_chunks * (blockIdx.z + 1) / a.slabs);
   const int nchunks = c_end - c_begin;
 
   if (warp == 0 && lane == 0) {
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
         int st = 0;
         uint32_t ph = 0;
         for (int ch = c_begin; ch < c_end; ++ch) {
-          const int t = ch * MC;
+          const int ub = ch / a.chunks_per_utt;
+          const int t = (ch - ub * a.chunks_per_utt) * MC;
           mbar_wait(empty_bar + st, ph ^ 1);
           uint8_t* sa = stage_base + (size_t)st * STAGE_BYTES;
           mbar_expect_tx(full_bar + st, STAGE_BYTES);
@@ -109,10 +111,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
         mbar_wait(conv_full, ph);
         ph ^= 1;
         tcgen05_fence_after();
-#pragma unroll
-        for (int tm = 0; tm < 6; ++tm) {
-          const int pa = (tm == 0 || tm == 1 || tm == 4) ? 0 : (tm == 5 ? 2 : 1);
-          const int py = (tm == 0 || tm == 2 || tm == 5) ? 0 : (tm == 4 ? 2 : 1);
+        for (int tm = 0; tm < a.nterms; ++tm) {
+          const int pa = (0x201100 >> (4 * tm)) & 0xF;
+          const int py = (0x021010 >> (4 * tm)) & 0xF;
           const uint64_t adesc = desc_hi | (uint64_t)(((pa0 + pa * A_BYTES) >> 4) & 0x3FFF);
           const uint64_t bdesc = desc_hi | (uint64_t)(((py0 + py * A_BYTES) >> 4) & 0x3FFF);
           umma_chunk(tmem_base, adesc, bdesc, idesc, accumulate, MC / UMMA_K);
@@ -123,9 +124,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
       umma_commit_elect<false>(smem_u32(tmem_full));
     } else if (warp < 2 + CONV_WARPS) {
       // ===================== converters: fp32 column -> three bf16 rows =====================
-      const int j = threadIdx.x - 64;          // 0..255
-      const bool isA = j < 128;
+      const int j = threadIdx.x - 64;          // 0..511
+      const bool isA = (j & 255) < 128;
       const int row = j & 127;                 // channel (k for A, n for dY) = row of the operand tile
+      const int mh = j >> 8;                   // which half of the chunk's 64 time steps
       const uint32_t src_off = (isA ? 0u : (uint32_t)STG_A) + (uint32_t)(row >> 5) * BOX_BYTES + (uint32_t)(row & 3) * 4;
       const uint32_t c4 = (uint32_t)(row & 31) >> 2;
       const uint32_t dst0 = smem_u32(planes) + (isA ? 0u : (uint32_t)PL_A) + (uint32_t)row * 128;
@@ -136,37 +138,27 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
       for (int ch = 0; ch < nchunks; ++ch) {
         mbar_wait(full_bar + st, ph);
         const uint32_t src = stage0 + (uint32_t)st * STAGE_BYTES + src_off;
-        uint32_t p1[32], p2[32], p3[32];
+        uint32_t p1[16], p2[16], p3[16];
 #pragma unroll
-        for (int m = 0; m < MC; m += 2) {
+        for (int m = 0; m < MC / 2; m += 2) {
           float x[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const uint32_t mm = (uint32_t)(m + e);
+            const uint32_t mm = (uint32_t)(32 * mh + m + e);
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[e]) : "r"(src + mm * 128 + ((c4 ^ (mm & 7)) << 4)));
           }
-          uint32_t h1[2], h2[2], h3[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {   // exact split: each step peels the leading 8 significand bits
-            h1[e] = __float_as_uint(x[e]) & 0xFFFF0000u;
-            const float r1 = x[e] - __uint_as_float(h1[e]);
-            h2[e] = __float_as_uint(r1) & 0xFFFF0000u;
-            h3[e] = __float_as_uint(r1 - __uint_as_float(h2[e]));
-          }
-          p1[m >> 1] = __byte_perm(h1[0], h1[1], 0x7632);
-          p2[m >> 1] = __byte_perm(h2[0], h2[1], 0x7632);
-          p3[m >> 1] = __byte_perm(h3[0], h3[1], 0x7632);
+          split3_pair(x[0], x[1], p1[m >> 1], p2[m >> 1], p3[m >> 1]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + st);    // staging slot consumed: the producer may refill it
         mbar_wait(planes_free, pf ^ 1);                // MMAs of the previous chunk have read the operand tiles
         pf ^= 1;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t off = ((uint32_t)g ^ sw) << 4;
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t off = ((uint32_t)(4 * mh + g) ^ sw) << 4;
           sts128(dst0 + off, make_uint4(p1[4 * g], p1[4 * g + 1], p1[4 * g + 2], p1[4 * g + 3]));
           sts128(dst0 + A_BYTES + off, make_uint4(p2[4 * g], p2[4 * g + 1], p2[4 * g + 2], p2[4 * g + 3]));
-          sts128(dst0 + 2 * A_BYTES + off, make_uint4(p3[4 * g], p3[4 * g + 1], p3[4 * g + 2], p3[4 * g + 3]));
+          if (a.nterms > 3) sts128(dst0 + 2 * A_BYTES + off, make_uint4(p3[4 * g], p3[4 * g + 1], p3[4 * g + 2], p3[4 * g + 3]));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -244,7 +236,7 @@ bool wgrad_tc3_supported(const WgradArgs& a) {
   return true;
 }
 
-int wgrad_tc3(const WgradArgs& w, cudaStream_t st) {
+int wgrad_tc3(const WgradArgs& w, int nterms, cudaStream_t st) {
   if (w.B <= 0 || w.Ti <= 0 || w.N <= 0) return 0;
   static bool configured = false;
   if (!configured) {
@@ -268,15 +260,17 @@ int wgrad_tc3(const WgradArgs& w, cudaStream_t st) {
     a.mapY[1] = a.mapY[0];
   }
   a.nseg = w.nseg; a.n0cols = n0cols; a.N = w.N; a.dW = w.dW; a.ldw = w.ldw; a.B = w.B; a.Ti = w.Ti;
+  a.nterms = nterms == 3 ? 3 : 6;
   a.chunks_per_utt = (w.Ti + wg3::MC - 1) / wg3::MC;
   const int ntiles = (w.N + wg3::BNW - 1) / wg3::BNW;
   const int64_t tiles = (int64_t)ktiles * ntiles;
   // one wave of CTAs if possible, but keep >= 4 chunks per slab so the epilogue (atomics) stays amortised
-  int64_t want = std::max<int64_t>(1, ((int64_t)num_sms() + tiles - 1) / tiles);
-  int per_utt = (int)std::max<int64_t>(1, std::min<int64_t>((want + w.B - 1) / w.B, std::max(1, a.chunks_per_utt / 4)));
-  a.slabs_per_utt = per_utt;
-  FWN_CHECK((int64_t)w.B * per_utt <= 65535 && ntiles <= 65535, "wgrad: grid too large");
-  dim3 grid((unsigned)ktiles, (unsigned)ntiles, (unsigned)(w.B * per_utt));
+  const int64_t total_chunks = (int64_t)w.B * a.chunks_per_utt;
+  int64_t slabs = std::max<int64_t>(1, (int64_t)num_sms() / tiles);                 // at most one wave of CTAs
+  slabs = std::max<int64_t>(1, std::min<int64_t>(slabs, total_chunks / 4));          // >= 4 chunks per slab
+  a.slabs = (int)slabs;
+  FWN_CHECK(slabs <= 65535 && ntiles <= 65535, "wgrad: grid too large");
+  dim3 grid((unsigned)ktiles, (unsigned)ntiles, (unsigned)slabs);
   wg3::wgrad_tc3_kernel<<<grid, wg3::THREADS, wg3::SMEM, st>>>(a);
   FWN_LAUNCH_CHECK();
   return 0;

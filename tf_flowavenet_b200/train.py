@@ -28,7 +28,7 @@ def learning_rate(global_step):
 class Trainer:
     """One tower.  `group`: torch.distributed process group over which tower gradients are averaged (None = single tower)."""
 
-    def __init__(self, model, group=None, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8, scale=1.0):
+    def __init__(self, model, group=None, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8, scale=1.0, split_terms=3):
         if model._precision != _lib.FWN_FP32:
             raise ValueError("training runs on the fp32 engines: use hparams.dtype='float32'")
         self.model, self.group = model, group
@@ -39,6 +39,8 @@ class Trainer:
         model._sync_params()
         with torch.cuda.device(model._device):
             _lib.check(L.fwn_train_enable(model._h, _lib.stream_ptr()))
+        # 3 bf16 product terms per fp32 product (~2^-16) for the training GEMMs, 6 (fp32 accuracy) for inference passes
+        _lib.check(L.fwn_set_split_terms(model._h, 6, int(split_terms)))
         self._n = L.fwn_grad_floats(model._h)
         self._np = L.fwn_param_floats(model._h)
         self.grads = torch.zeros(self._n, dtype=torch.float32, device=model._device)
