@@ -372,12 +372,12 @@ static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const T
     a.nseg = nseg;
     a.dY0 = y0; a.ld0 = ld0; a.n0cols = n0; a.dY1 = y1; a.ld1 = ld1; a.N = N;
     a.dW = gw(m, P); a.ldw = ldw; a.B = B; a.Ti = Ti;
-    m->launches += 2;
-    if (wgrad_on_tensor_cores() && wgrad_tc3_supported(a)) {
-      if (wgrad_tc3(a, m->cur_terms, st)) return 1;
-    } else if (wgrad(a, st)) {
-      return 1;
+    if (wgrad_on_tensor_cores() && wgrad_tc3_supported(a)) {   // bias gradient (column sums of dY) fused into the same kernel
+      m->launches += 1;
+      return wgrad_tc3(a, gw(m, bias_slot), m->cur_terms, st);
     }
+    m->launches += 2;
+    if (wgrad(a, st)) return 1;
     return colsum(y0, ld0, n0, y1, ld1, N, rows, gw(m, bias_slot), st);
   };
 

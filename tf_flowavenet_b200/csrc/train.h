@@ -61,7 +61,7 @@ int adam_update(float* p, float* m, float* v, const float* g, const float* norm,
 
 // ---- wgrad_tc3.cu (tensor-core wgrad, fp32-accurate)
 bool wgrad_tc3_supported(const WgradArgs& a);
-int wgrad_tc3(const WgradArgs& a, int nterms, cudaStream_t st);
+int wgrad_tc3(const WgradArgs& a, float* dbias, int nterms, cudaStream_t st);
 
 // ---- gemm_tc3.cu
 bool tc3_supported(const GemmArgs& g);

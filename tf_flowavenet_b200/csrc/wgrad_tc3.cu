@@ -40,6 +40,7 @@ struct alignas(64) Wg3Args {
   int nseg, n0cols, N;
   float* dW;
   int64_t ldw;
+  float* dbias;          // nullable: column sums of dY (bias gradient), accumulated by the CTAs of the first K tile
   int B, Ti, chunks_per_utt, slabs;   // slab = contiguous range of (utterance, chunk) pairs
   int nterms;   // 6 or 3, as in gemm_tc3.cu
 };
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
       const uint32_t dst0 = smem_u32(planes) + (isA ? 0u : (uint32_t)PL_A) + (uint32_t)row * 128;
       const uint32_t sw = (uint32_t)(row & 7);
       const uint32_t stage0 = smem_u32(stage_base);
+      float bsum = 0.f;   // dY converters: running column sum = bias gradient
       int st = 0;
       uint32_t ph = 0, pf = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
             const uint32_t mm = (uint32_t)(32 * mh + m + e);
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[e]) : "r"(src + mm * 128 + ((c4 ^ (mm & 7)) << 4)));
           }
+          bsum += x[0] + x[1];
           split3_pair(x[0], x[1], p1[m >> 1], p2[m >> 1], p3[m >> 1]);
         }
         __syncwarp();
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(conv_full);
         if (++st == NST) { st = 0; ph ^= 1; }
       }
+      if (!isA && a.dbias && blockIdx.x == 0 && n0 + row < a.N) atomicAdd(a.dbias + n0 + row, bsum);
     } else {
       // ===================== epilogue: TMEM -> shared (transpose) -> coalesced fp32 atomics =====================
       const int lg = warp & 3;
@@ -236,7 +240,7 @@ bool wgrad_tc3_supported(const WgradArgs& a) {
   return true;
 }
 
-int wgrad_tc3(const WgradArgs& w, int nterms, cudaStream_t st) {
+int wgrad_tc3(const WgradArgs& w, float* dbias, int nterms, cudaStream_t st) {
   if (w.B <= 0 || w.Ti <= 0 || w.N <= 0) return 0;
   static bool configured = false;
   if (!configured) {
@@ -259,6 +263,7 @@ int wgrad_tc3(const WgradArgs& w, int nterms, cudaStream_t st) {
   } else {
     a.mapY[1] = a.mapY[0];
   }
+  a.dbias = dbias;
   a.nseg = w.nseg; a.n0cols = n0cols; a.N = w.N; a.dW = w.dW; a.ldw = w.ldw; a.B = w.B; a.Ti = w.Ti;
   a.nterms = nterms == 3 ? 3 : 6;
   a.chunks_per_utt = (w.Ti + wg3::MC - 1) / wg3::MC;
