@@ -9,8 +9,11 @@ What it restates (reference file:line):
   * tf.clip_by_global_norm(grads, 1)                                                       train.py:27-32
   * learning-rate schedule 1e-3, /2, /4, /6 at 200k/400k/600k steps                        train.py:15-24
   * tf.train.AdamOptimizer(lr) defaults beta1=.9 beta2=.999 eps=1e-8                       train.py:22, [TF] adam.py
-Parity status: the forward graph is pinned (tests/golden); tf.gradients itself cannot run here (TF 1.12 is not installable),
-so gradient parity is "autograd of the pinned graph", cross-checked by finite differences in tests/test_train_oracle.py.
+Parity status: PINNED.  tests/golden/*_grads.npz hold tf.gradients(loss, tf.trainable_variables()) of the reference's own
+model.py (imported unmodified, train.py:59-63 replayed literally) run on the eager TF shim (tests/golden/make_golden_grads.py);
+tests/test_train_oracle.py checks this oracle against them (norm and probed entries of every variable's gradient, global norm)
+and against central finite differences.  TensorFlow 1.12 itself is not installable here, so "reference" means the reference's
+Python graph code over the shim's restatement of the TF ops (same status as the forward fixtures).
 """
 from typing import Dict, Tuple
 

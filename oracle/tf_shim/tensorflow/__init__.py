@@ -89,6 +89,24 @@ def set_presets(d):
     _state["unused_presets"] = set(d)
 
 
+def set_trainable(flag):
+    """Shim switch: variables created afterwards take part in tf.gradients (torch autograd leaves)."""
+    _state["trainable"] = bool(flag)
+
+
+def trainable_variables():
+    return [v for v in _state["vars"].values() if v.requires_grad]
+
+
+def gradients(ys, xs, **kw):
+    """tf.gradients(ys, xs): symbolic gradient == torch.autograd.grad over the eagerly recorded graph; None where unconnected."""
+    return list(_torch.autograd.grad(ys, list(xs), allow_unused=True))
+
+
+def scalar_mul(scalar, x):
+    return x * scalar
+
+
 def global_variables_dict():
     return dict(_state["vars"])
 
@@ -157,6 +175,8 @@ def get_variable(name, shape=None, dtype=float32, initializer=None, trainable=Tr
         init = initializer if initializer is not None else initializers.glorot_uniform()
         val = init(shape, dtype)
     v = val.clone().as_subclass(Variable)
+    if _state.get("trainable") and trainable:
+        v.requires_grad_(True)
     _state["vars"][full] = v
     return v
 

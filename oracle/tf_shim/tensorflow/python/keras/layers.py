@@ -43,7 +43,8 @@ class Conv2DTranspose(_ConvBase):
     def call(self, inputs):
         """[TF] keras Conv2DTranspose.call, channels_last, padding 'same': output spatial = input * stride and
         nn.conv2d_transpose == conv2d_backprop_input, i.e. the gradient w.r.t. the input of the SAME-padded
-        forward conv (kernel [kh,kw,out_ch,in_ch]).  Computed literally as that gradient via autograd."""
+        forward conv (kernel [kh,kw,out_ch,in_ch]).  Computed literally as that gradient via autograd (create_graph keeps it
+        differentiable w.r.t. the kernel and the input, for tf.gradients)."""
         assert self.padding == "same" and self.data_format == "channels_last"
         b, h, w, cin = inputs.shape
         kh, kw, cout, _ = self.kernel.shape
@@ -53,10 +54,10 @@ class Conv2DTranspose(_ConvBase):
         pw = max((w - 1) * sw + kw - wo, 0)
         img = torch.zeros(b, cout, ho, wo, dtype=inputs.dtype, requires_grad=True)
         padded = torch.nn.functional.pad(img, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
-        k = self.kernel.detach().as_subclass(torch.Tensor).permute(3, 2, 0, 1)  # [in_ch(out of fwd conv), out_ch, kh, kw]
+        k = self.kernel.as_subclass(torch.Tensor).permute(3, 2, 0, 1)  # [in_ch(out of fwd conv), out_ch, kh, kw]
         y = torch.nn.functional.conv2d(padded, k, stride=(sh, sw))
         assert tuple(y.shape) == (b, cin, h, w), (y.shape, inputs.shape)
-        (grad,) = torch.autograd.grad(y, img, grad_outputs=inputs.detach().as_subclass(torch.Tensor).permute(0, 3, 1, 2).contiguous())
+        (grad,) = torch.autograd.grad(y, img, grad_outputs=inputs.as_subclass(torch.Tensor).permute(0, 3, 1, 2).contiguous(), create_graph=True)
         import tensorflow as tf
         out = tf.convert_to_tensor(grad.permute(0, 2, 3, 1).contiguous())
         if self.use_bias:

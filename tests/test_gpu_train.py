@@ -48,6 +48,31 @@ def test_gradients_match_oracle(case, terms):
     assert float((tr.grads - g1).abs().max()) <= 1e-4 * float(g1.abs().max())
 
 
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_gradients_match_reference_fixture(case):
+    """Against tf.gradients of the reference's own model.py run on the TF shim (tests/golden/make_golden_grads.py, train.py:59-63):
+    per-variable gradient norms and probed entries."""
+    import os
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load(case)
+    gx = np.load(os.path.join(os.path.dirname(__file__), "golden", case + "_grads.npz"))
+    tr = T.Trainer(make_model(hp, params), split_terms=6)
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    log_p, logdet = tr.loss_and_grads(x, c)
+    assert abs(float(-(log_p + logdet)) - float(gx["loss"])) < 1e-4 * max(1.0, abs(float(gx["loss"])))
+    norm = torch.zeros(1, device="cuda")
+    got = tr.gradients()
+    gmax = max(float(gx["norm::" + k]) for k in got)
+    sq = 0.0
+    for k, g in got.items():
+        flat = g.reshape(-1).double().cpu().numpy()
+        n = float(gx["norm::" + k])
+        sq += float((flat * flat).sum())
+        assert abs(float(np.sqrt((flat * flat).sum())) - n) <= 2e-4 * max(n, 1e-6 * gmax), k
+        np.testing.assert_allclose(flat[gx["idx::" + k]], gx["val::" + k], rtol=0, atol=2e-4 * max(n, 1e-6 * gmax), err_msg=k)
+    assert abs(np.sqrt(sq) - float(gx["global_norm"])) < 1e-4 * float(gx["global_norm"])
+
+
 def test_device_repack_equals_host_prepack():
     """fwn_train_enable re-derives every operand on the device; the forward result must stay on the golden values, and a
     forward in inference mode after it (same handle) as well."""

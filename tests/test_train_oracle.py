@@ -68,3 +68,32 @@ def test_clip_average_adam():
     v = {"a": torch.zeros(2, dtype=torch.float64)}
     new = TO.adam_step(p, {"a": torch.tensor([0.5, -2.0], dtype=torch.float64)}, m, v, 1e-3, 1)
     assert torch.allclose(new["a"], torch.tensor([-1e-3, 1e-3], dtype=torch.float64), rtol=1e-6)
+
+
+import pytest  # noqa: E402
+
+from tests._golden import load  # noqa: E402
+
+GRAD_CASES = ["g1_b2f2l2", "g2_b3f2l1", "g4_causal", "g5_additive", "g6_l3"]
+
+
+def load_grads(case):
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", case + "_grads.npz"))
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_oracle_gradients_match_reference_fixture(case):
+    """tests/golden/*_grads.npz hold tf.gradients(loss, trainable_variables) of the reference's own model.py (train.py:59-63) run on
+    the TF shim (make_golden_grads.py): this pins the training oracle the same way the forward fixtures pin the forward oracle."""
+    hp, params, fx = load(case)
+    gx = load_grads(case)
+    loss, log_p, logdet, grads = TO.loss_and_grads(params, hp, torch.from_numpy(fx["x"]), torch.from_numpy(fx["c"]))
+    assert abs(loss - float(gx["loss"])) < 1e-6 * max(1.0, abs(loss))  # the reference returns float32 scalars (model.py:345-347)
+    # the reference keeps ActNorm variables and the returned scalars in float32 (model.py:24-27,345-347): agreement to ~1e-7
+    assert abs(TO.global_norm(grads) - float(gx["global_norm"])) < 1e-6 * float(gx["global_norm"])
+    for k, g in grads.items():
+        flat = g.reshape(-1).numpy()
+        n = float(gx["norm::" + k])
+        assert abs(float(np.sqrt((flat * flat).sum())) - n) <= 1e-6 * max(n, 1e-12), k
+        np.testing.assert_allclose(flat[gx["idx::" + k]], gx["val::" + k], rtol=1e-5, atol=1e-6 * max(n, 1e-12), err_msg=k)
