@@ -423,7 +423,9 @@ def main():
     value = samples_per_step * args.steps / (ms * 1e-3)
     g_ms, g_n, g_flop = prof["gate_gemm"]
     ach = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    roof = {"kernel": "tc_gemm_kernel<EPI_GATE,256> (dilated conv k=3 + cond 1x1 + tanh*sigmoid)" if dtype == "bfloat16" else "simt_gemm_kernel<EPI_GATE>",
+    roof = {"kernel": "tc_gemm_kernel<EPI_GATE,256> (dilated conv k=3 + cond 1x1 + tanh*sigmoid)" if dtype == "bfloat16" else
+            ("simt_gemm_kernel<EPI_GATE>" if os.environ.get("FWN_FP32_ENGINE") == "simt" else
+             "tc3_gemm_kernel<EPI_GATE,128> (fp32 parity mode: 6 bf16 MMA terms per product, so <= 1/6 of the bf16 peak is attainable)"),
             "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
             "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["src"], "traffic": None,
             "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / ms_prof,

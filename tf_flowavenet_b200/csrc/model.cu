@@ -686,7 +686,7 @@ int model_plan(const Model* m, int B, int T, Workspace* w, char* base) {
   w->o = take(M0 * F * as);
   w->s = take(M0 * F * as);
   w->u = take(M0 * F * as);
-  w->a0 = take(c.precision == FWN_MIXED_BF16 ? (size_t)B * T * 8 : 0);  // rows_i * ceil8(nq_i) * 2 bytes <= 8*B*T
+  w->a0 = take((size_t)B * T * 8);  // mixed: rows_i * ceil8(nq_i) * 2 bytes; fp32: rows_i * ceil4(nq_i) * 4 bytes; both <= 8*B*T
   w->bytes = off;
   return 0;
 }
@@ -792,6 +792,15 @@ int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, i
   return 0;
 }
 
+static bool fp32_front_on_tensor_cores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_FP32_ENGINE");
+    v = (e && !strcmp(e, "simt")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // One coupling WaveNet + the in-place flow update of X (ActNorm + AffineCoupling [+ change_order absorbed]).
 int finish_forward(const double* sums, const double* an_logdet, float* logp_out, float* logdet_out, double n, cudaStream_t st) {
   finish_forward_kernel<<<1, 1, 0, st>>>(sums, an_logdet, logp_out, logdet_out, n);
@@ -813,7 +822,19 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   for (int k = 0; k < 3; ++k) fa.shift[k] = shift_of(k, 1);
   const double rows = (double)B * Ti;
   prof_begin(m, PROF_FRONT, 2.0 * rows * 3 * fp.nq * F, st);
-  if (!bf16) {
+  if (!bf16 && fp.w3[GEMM_FRONT].p && fp32_front_on_tensor_cores()) {
+    // fp32 mode: gather (+ActNorm) the pass-through half, then the front conv is three time-shifted K segments on the split engine
+    const int kq = (fp.nq + 3) / 4 * 4;
+    m->launches++;
+    if (front_pack_f32(X, fp.Cx, fp.nq, kq, fp.off2log, fa.an_b, fa.an_s, reinterpret_cast<float*>(w.a0), (int64_t)B * Ti, st)) return 1;
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    for (int k = 0; k < 3; ++k) g.seg[k] = Seg{w.a0, kq, fa.shift[k], fp.nq, k * fp.front_k16};
+    g.nseg = 3;
+    g.W = fp.front_w; g.ldw = F; g.N = F;
+    g.e.bias = fp.front_b; g.e.out0 = w.h0; g.e.ld = F; g.e.relu = 1; g.e.F = F;
+    if (run_gemm(m, g, EPI_PLAIN, GEMM_FRONT, fp, st)) return 1;
+  } else if (!bf16) {
     m->launches++;
     if (front_conv(fa, false, st)) return 1;
   } else {

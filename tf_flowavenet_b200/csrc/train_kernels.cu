@@ -440,7 +440,9 @@ __global__ void front_pack_f32_kernel(const float* __restrict__ X, int Cx, int n
     const int o = (int)(i - row * Cx);
     const int q = __ldg(off2log + o);
     if (q >= nq) continue;
-    A0[row * kq + q] = (__ldg(X + i) + __ldg(an_b + o)) * __ldg(an_s + o);
+    float v = __ldg(X + i);
+    if (an_b) v = (v + __ldg(an_b + o)) * __ldg(an_s + o);   // forward direction: ActNorm on load; reverse: identity
+    A0[row * kq + q] = v;
   }
 }
 int front_pack_f32(const float* X, int Cx, int nq, int kq, const int* off2log, const float* an_b, const float* an_s, float* A0, int64_t rows,
