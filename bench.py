@@ -154,12 +154,12 @@ def main_train(args):
         samples, secs, thr = oracle_train_step(hp_kw, 1, n_frames)
         val = samples / secs
         sample = "1 utterance x %d frames (%d samples): loss + autograd gradients of the same model, fp32, best of 2 after 1 warm-up" % (n_frames, samples)
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        emit({"impl": "reference", "metric": metric, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": "samples/s", "cores": thr, "kind": "port", "sample": sample,
                                            "note": "CPU restatement (PyTorch-CPU autograd) of the reference training graph; optimizer update not included"},
-                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -266,12 +266,35 @@ def main_train(args):
         line["cpu_baseline"] = {"value": samples / secs, "unit": "samples/s", "cores": thr, "kind": "port",
                                 "sample": "1 utterance x %d frames (%d samples): loss + autograd gradients, fp32, best of 2 after 1 warm-up" % (n_frames, samples),
                                 "note": "CPU restatement (PyTorch-CPU autograd) of the reference training graph; baseline only"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr while the benchmark runs (NCCL prints its version banner to stdout on the first multi-rank collective);
+    emit() writes the one JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -304,13 +327,13 @@ def main():
         samples, secs, thr = oracle_step(hp_kw, direction, sb, sf)
         val = samples / secs
         sample = "%d utterance(s) x %d frames (%d samples) of the same model, fp32, best of 3 after 1 warm-up" % (sb, sf, samples)
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        emit({"impl": "reference", "metric": metric, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": "samples/s", "cores": thr, "kind": "port", "sample": sample,
                                            "note": "CPU restatement of the reference TF-1.12 graph (PyTorch-CPU); TF 1.12 is not installable on Python 3.12"},
                           "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "xrt_at_22050": val / 22050.0}))
+                          "xrt_at_22050": val / 22050.0})
         return
 
     import torch
@@ -457,7 +480,7 @@ def main():
         line["cpu_baseline"] = {"value": samples / secs, "unit": "samples/s", "cores": thr, "kind": "port",
                                 "sample": "%d utterance(s) x %d frames (%d samples) of the same model, fp32, best of 3 after 1 warm-up" % (sb, sf, samples),
                                 "note": "CPU restatement of the reference TF-1.12 graph (PyTorch-CPU); baseline only"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
