@@ -144,3 +144,32 @@ def test_training_needs_fp32_and_enable():
     hp, params, fx = load("g1_b2f2l2")
     with pytest.raises(ValueError):
         T.Trainer(make_model(hp, params, dtype="bfloat16"))
+
+
+def test_two_stream_backward_equals_single_stream_at_full_depth():
+    """The backward pass runs weight gradients and the conditioning gradient on a side stream (event-ordered, double-buffered
+    scratch).  Same gradients as the single-stream order on the full hparams.py model at the C5 shape, up to fp32 atomics order."""
+    import os
+    import tf_flowavenet_b200 as P
+    import tf_flowavenet_b200.train as T
+    from tf_flowavenet_b200.synthetic import synthetic_inputs, synthetic_params
+    net = P.FloWaveNet(P.HParams(**{**P.hparams.values(), "dtype": "float32"}), variables=P.VariableStore())
+    net.load_variables(synthetic_params(net.variable_shapes(), seed=5))
+    x, c = synthetic_inputs(256, 80, 8, 25, 6, "x")
+    x, c = torch.from_numpy(x).cuda(), torch.from_numpy(c).cuda()
+    net.initialize_actnorm(x, c)
+    tr = T.Trainer(net)
+    res = {}
+    try:
+        for mode in ("1", "0", "0"):
+            os.environ["FWN_TRAIN_STREAMS"] = mode
+            tr.loss_and_grads(x, c)
+            torch.cuda.synchronize()
+            res.setdefault(mode, []).append(tr.grads[:tr._np].clone())
+    finally:
+        os.environ.pop("FWN_TRAIN_STREAMS", None)
+    single, dual_a, dual_b = res["1"][0], res["0"][0], res["0"][1]
+    scale = float(single.abs().max())
+    assert float((dual_a - single).abs().max()) < 1e-4 * scale
+    assert float((dual_b - dual_a).abs().max()) < 1e-4 * scale
+    assert abs(float(dual_a.double().norm()) - float(single.double().norm())) < 1e-5 * float(single.double().norm())

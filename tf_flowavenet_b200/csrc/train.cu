@@ -40,6 +40,20 @@ struct TrainState {
   double* scratch = nullptr;  // [8]
   float* norm = nullptr;      // [1]
   float* up_dw = nullptr;     // [max 2s*3 + 1]
+  // backward pass: weight gradients and the conditioning gradient are off the critical chain of dgrads -> low-priority side stream
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_next = 0;
+  cudaEvent_t set_done[2] = {nullptr, nullptr};
+  cudaEvent_t next_event() {
+    if (ev.empty()) {
+      ev.resize(64);
+      for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    cudaEvent_t e = ev[ev_next];
+    ev_next = (ev_next + 1) % ev.size();
+    return e;
+  }
 };
 
 void train_free(Model* m) {
@@ -48,6 +62,9 @@ void train_free(Model* m) {
   cudaFree(t->what); cudaFree(t->wmap); cudaFree(t->gwall); cudaFree(t->d_folds); cudaFree(t->d_fwork); cudaFree(t->d_pdesc);
   cudaFree(t->d_pwork); cudaFree(t->d_an); cudaFree(t->planes); cudaFree(t->adam_m); cudaFree(t->adam_v); cudaFree(t->scratch);
   cudaFree(t->norm); cudaFree(t->up_dw);
+  for (auto e : t->ev) cudaEventDestroy(e);
+  for (auto e : t->set_done) if (e) cudaEventDestroy(e);
+  if (t->side) cudaStreamDestroy(t->side);
   delete t;
   m->train = nullptr;
 }
@@ -174,6 +191,10 @@ static int train_build(Model* m) {
   int smax = 2;
   for (int i = 0; i < c.n_upsample; ++i) smax = std::max(smax, c.upsample_scales[i]);
   FWN_CUDA(cudaMalloc(&t->up_dw, (size_t)(2 * smax * 3 + 1) * sizeof(float)));
+  int lo = 0, hi = 0;
+  FWN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = numerically greatest = lowest priority
+  FWN_CUDA(cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, lo));
+  for (auto& e : t->set_done) FWN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
 
@@ -216,7 +237,7 @@ struct TrainWs {
   double* sums;
   double* ddi;
   float *X, *dX, *up0, *dup0, *cA, *cB, *dcA, *dcB;
-  float *dnet, *da0, *du, *ds, *dfg, *r[2];
+  struct BwdSet { float *dnet, *da0, *du, *ds; float* dfg[MAX_LAYERS]; float* r[MAX_LAYERS]; } set[2];   // alternate per flow
   std::vector<Tape> tape;
   size_t bytes;
 };
@@ -244,8 +265,11 @@ static int train_plan(const Model* m, int B, int T, TrainWs* w, char* base) {
   w->up0 = take(up_elems);
   w->dup0 = take(up_elems);
   w->cA = take(BT * H); w->cB = take(BT * H); w->dcA = take(BT * H); w->dcB = take(BT * H);
-  w->dnet = take(2 * BT); w->da0 = take(2 * BT);
-  w->du = take(M0 * F); w->ds = take(M0 * F); w->dfg = take(M0 * 2 * F); w->r[0] = take(M0 * F); w->r[1] = take(M0 * F);
+  for (auto& bs : w->set) {
+    bs.dnet = take(2 * BT); bs.da0 = take(2 * BT);
+    bs.du = take(M0 * F); bs.ds = take(M0 * F);
+    for (int n = 0; n < L; ++n) { bs.dfg[n] = take(M0 * 2 * F); bs.r[n] = take(M0 * F); }
+  }
   w->tape.assign(m->flows.size(), Tape{});
   for (int i = 0; i < c.n_block; ++i) {
     const size_t M = BT >> (i + 1);
@@ -355,8 +379,28 @@ static float* gw(const Model* m, const void* P) {  // gradient slot mirroring a 
   return m->train->gwall + (reinterpret_cast<const float*>(P) - reinterpret_cast<const float*>(m->pack));
 }
 
+// FWN_TRAIN_STREAMS=1 keeps the whole backward pass on the caller's stream (diagnostics / A-B timing)
+static bool dual_stream() {   // read per call: tests flip it between two passes of one process
+  const char* e = getenv("FWN_TRAIN_STREAMS");
+  return !(e && e[0] == '1');
+}
+
 static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const TrainFlow& tf, const Tape& tp, const float* Xpost, int B,
-                         int Ti, float* G, cudaStream_t st) {
+                         int Ti, float* G, int parity, cudaStream_t st) {
+  TrainState* t = m->train;
+  const bool dual = dual_stream();
+  cudaStream_t s1 = dual ? t->side : st;   // weight gradients + conditioning gradient
+  const TrainWs::BwdSet& bs = w.set[parity];
+  // everything issued so far on the main stream becomes visible to the side stream
+  auto fork = [&]() -> int {
+    if (!dual) return 0;
+    cudaEvent_t e = t->next_event();
+    FWN_CUDA(cudaEventRecord(e, st));
+    FWN_CUDA(cudaStreamWaitEvent(s1, e, 0));
+    return 0;
+  };
+  // this flow reuses the scratch set of the flow two steps back: its side-stream readers must be done
+  if (dual) FWN_CUDA(cudaStreamWaitEvent(st, t->set_done[parity], 0));
   const fwn_config& c = m->cfg;
   const int F = c.filter_size, L = c.n_layer, nq = fp.nq, nq4 = ceil4(nq), ldn = ceil4(2 * nq);
   const int64_t rows = (int64_t)B * Ti;
@@ -374,76 +418,80 @@ static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const T
     a.dW = gw(m, P); a.ldw = ldw; a.B = B; a.Ti = Ti;
     if (wgrad_on_tensor_cores() && wgrad_tc3_supported(a)) {   // bias gradient (column sums of dY) fused into the same kernel
       m->launches += 1;
-      return wgrad_tc3(a, gw(m, bias_slot), m->cur_terms, st);
+      return wgrad_tc3(a, gw(m, bias_slot), m->cur_terms, s1);
     }
     m->launches += 2;
-    if (wgrad(a, st)) return 1;
-    return colsum(y0, ld0, n0, y1, ld1, N, rows, gw(m, bias_slot), st);
+    if (wgrad(a, s1)) return 1;
+    return colsum(y0, ld0, n0, y1, ld1, N, rows, gw(m, bias_slot), s1);
   };
 
   // 1. coupling: d out_b -> (d log_s, d t), d b
   m->launches++;
-  if (affine_bwd(w.dX, Xpost, tp.net, ldn, w.dnet, rows, fp.Cx, nq, fp.b_off, n_total, st)) return 1;
+  if (affine_bwd(w.dX, Xpost, tp.net, ldn, bs.dnet, rows, fp.Cx, nq, fp.b_off, n_total, st)) return 1;
+  if (fork()) return 1;
   // 2. zero conv
   {
     Seg s0{tp.u, F, 0, F, 0};
-    if (wg(&s0, 1, w.dnet, ldn, 2 * nq, nullptr, 0, 2 * nq, fp.zero_w, 2 * nq, fp.zero_b)) return 1;
+    if (wg(&s0, 1, bs.dnet, ldn, 2 * nq, nullptr, 0, 2 * nq, fp.zero_w, 2 * nq, fp.zero_b)) return 1;
     GemmArgs g = {};
-    g.seg[0] = Seg{w.dnet, ldn, 0, 2 * nq, 0};
+    g.seg[0] = Seg{bs.dnet, ldn, 0, 2 * nq, 0};
     g.nseg = 1; g.N = F;
-    linear(g, w.du, F, nullptr, tp.u, 1.f);   // through relu(final(..))
+    linear(g, bs.du, F, nullptr, tp.u, 1.f);   // through relu(final(..))
     if (bw_gemm(m, g, EPI_LINEAR, tf.zero_T, st)) return 1;
+    if (fork()) return 1;
   }
   // 3. final conv
   {
     Seg s0{tp.s, F, 0, F, 0};
-    if (wg(&s0, 1, w.du, F, F, nullptr, 0, F, fp.final_w, F, fp.final_b)) return 1;
+    if (wg(&s0, 1, bs.du, F, F, nullptr, 0, F, fp.final_w, F, fp.final_b)) return 1;
     GemmArgs g = {};
-    g.seg[0] = Seg{w.du, F, 0, F, 0};
+    g.seg[0] = Seg{bs.du, F, 0, F, 0};
     g.nseg = 1; g.N = F;
-    linear(g, w.ds, F, nullptr, tp.s, 1.f);   // through relu(sum of skips): the gradient of every layer's skip output
+    linear(g, bs.ds, F, nullptr, tp.s, 1.f);   // through relu(sum of skips): the gradient of every layer's skip output
     if (bw_gemm(m, g, EPI_LINEAR, tf.final_T, st)) return 1;
   }
   // 4. residual layers, last to first.  r = gradient of the layer's residual-conv output = sqrt(.5) * d h_{n+1}
   const float* cond = fp.cond_half == 0 ? w.cA : w.cB;
   float* dcond = fp.cond_half == 0 ? w.dcA : w.dcB;
-  int cur = 0;
   int d = 1;
   for (int n = 1; n < L; ++n) d *= 3;
   for (int n = L - 1; n >= 0; --n, d /= 3) {
     const bool last = n == L - 1;
-    const float* r = w.r[cur];
-    float* rnext = w.r[cur ^ 1];
+    const float* r = last ? nullptr : bs.r[n + 1];   // written by the previous iteration (layer n+1)
+    float* rnext = bs.r[n];
+    float* dfg = bs.dfg[n];
+    if (fork()) return 1;                             // ds (and r) are ready for the res|skip weight gradient
     {
       Seg s0{tp.o[n], F, 0, F, 0};
-      if (last) { if (wg(&s0, 1, w.ds, F, F, nullptr, 0, F, fp.rs_w[n], F, fp.rs_b[n])) return 1; }
-      else if (wg(&s0, 1, r, F, F, w.ds, F, 2 * F, fp.rs_w[n], 2 * F, fp.rs_b[n])) return 1;
+      if (last) { if (wg(&s0, 1, bs.ds, F, F, nullptr, 0, F, fp.rs_w[n], F, fp.rs_b[n])) return 1; }
+      else if (wg(&s0, 1, r, F, F, bs.ds, F, 2 * F, fp.rs_w[n], 2 * F, fp.rs_b[n])) return 1;
       GemmArgs g = {};
-      if (last) { g.seg[0] = Seg{w.ds, F, 0, F, 0}; g.nseg = 1; }
-      else { g.seg[0] = Seg{r, F, 0, F, 0}; g.seg[1] = Seg{w.ds, F, 0, F, F}; g.nseg = 2; }
+      if (last) { g.seg[0] = Seg{bs.ds, F, 0, F, 0}; g.nseg = 1; }
+      else { g.seg[0] = Seg{r, F, 0, F, 0}; g.seg[1] = Seg{bs.ds, F, 0, F, F}; g.nseg = 2; }
       g.N = F; g.B = B; g.Ti = Ti;
-      g.e.in0 = tp.fg[n]; g.e.out0 = w.dfg; g.e.F = F;
+      g.e.in0 = tp.fg[n]; g.e.out0 = dfg; g.e.F = F;
       if (bw_gemm(m, g, EPI_GATE_BWD, tf.rs_T[n], st)) return 1;
+      if (fork()) return 1;
     }
     {
       Seg sg[4];
       for (int k = 0; k < 3; ++k) sg[k] = Seg{tp.h[n], F, shift_of(c, k, d), F, k * F};
       sg[3] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
-      if (wg(sg, 4, w.dfg, 2 * F, 2 * F, nullptr, 0, 2 * F, fp.gate_w[n], 2 * F, fp.gate_b[n])) return 1;
+      if (wg(sg, 4, dfg, 2 * F, 2 * F, nullptr, 0, 2 * F, fp.gate_w[n], 2 * F, fp.gate_b[n])) return 1;
       GemmArgs gc = {};
-      gc.seg[0] = Seg{w.dfg, 2 * F, 0, 2 * F, 0};
+      gc.seg[0] = Seg{dfg, 2 * F, 0, 2 * F, 0};
       gc.nseg = 1; gc.N = fp.Kc;
       linear(gc, dcond, fp.Kc, dcond, nullptr, 1.f);   // accumulate the conditioning gradient in place
-      if (bw_gemm(m, gc, EPI_LINEAR, tf.cond_T[n], st)) return 1;
+      if (bw_gemm(m, gc, EPI_LINEAR, tf.cond_T[n], s1)) return 1;
       GemmArgs gh = {};
-      for (int k = 0; k < 3; ++k) gh.seg[k] = Seg{w.dfg, 2 * F, -shift_of(c, k, d), 2 * F, k * 2 * F};
+      for (int k = 0; k < 3; ++k) gh.seg[k] = Seg{dfg, 2 * F, -shift_of(c, k, d), 2 * F, k * 2 * F};
       gh.nseg = 3; gh.N = F;
       linear(gh, rnext, F, last ? nullptr : r, n == 0 ? tp.h[0] : nullptr, n > 0 ? 0.70710678118654752440f : 1.f);
       if (bw_gemm(m, gh, EPI_LINEAR, tf.gate_T[n], st)) return 1;
     }
-    cur ^= 1;
   }
-  const float* dh0 = w.r[cur];   // gradient of the front conv's pre-activation
+  const float* dh0 = bs.r[0];   // gradient of the front conv's pre-activation
+  if (fork()) return 1;
   // 5. front conv
   {
     Seg sg[3];
@@ -452,14 +500,16 @@ static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const T
     GemmArgs g = {};
     for (int k = 0; k < 3; ++k) g.seg[k] = Seg{dh0, F, -shift_of(c, k, 1), F, k * F};
     g.nseg = 3; g.N = nq;
-    if (nq4 != nq) FWN_CUDA(cudaMemsetAsync(w.da0, 0, (size_t)rows * nq4 * 4, st));
-    linear(g, w.da0, nq4, nullptr, nullptr, 1.f);
+    if (nq4 != nq) FWN_CUDA(cudaMemsetAsync(bs.da0, 0, (size_t)rows * nq4 * 4, st));
+    linear(g, bs.da0, nq4, nullptr, nullptr, 1.f);
     if (bw_gemm(m, g, EPI_LINEAR, tf.front_T, st)) return 1;
   }
   // 6. ActNorm (+ the WaveNet-input gradient on the pass-through half)
   m->launches++;
-  return actnorm_bwd(w.dX, w.da0, nq4, tp.xpre, fp.an_b, fp.an_s, fp.off2log, rows, fp.Cx, nq, G + (fp.raw_b - m->raw),
-                     G + (fp.raw_logs - m->raw), st);
+  if (actnorm_bwd(w.dX, bs.da0, nq4, tp.xpre, fp.an_b, fp.an_s, fp.off2log, rows, fp.Cx, nq, G + (fp.raw_b - m->raw),
+                     G + (fp.raw_logs - m->raw), st)) return 1;
+  if (dual) FWN_CUDA(cudaEventRecord(t->set_done[parity], s1));   // side-stream readers of this scratch set
+  return 0;
 }
 
 int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int32_t* gspk, int B, int T, float* logp_out, float* logdet_out,
@@ -496,14 +546,25 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   if (sumsq(w.X, w.sums + 1, (int64_t)BT, st)) return 1;
   if (finish_forward(w.sums, m->d_an_logdet, logp_out, logdet_out, (double)BT, st)) return 1;
   // ---- backward
+  if (dual_stream()) {
+    for (auto& e : t->set_done) FWN_CUDA(cudaEventRecord(e, st));   // nothing pending on either scratch set; also orders the memsets above
+    cudaEvent_t e = t->next_event();
+    FWN_CUDA(cudaEventRecord(e, st));
+    FWN_CUDA(cudaStreamWaitEvent(t->side, e, 0));
+  }
   m->launches++;
   if (logp_bwd(w.X, w.dX, (int64_t)BT, st)) return 1;
   for (int i = c.n_block - 1; i >= 0; --i)
     for (int j = c.n_flow - 1; j >= 0; --j) {
       const size_t f = (size_t)i * c.n_flow + j;
       const float* Xpost = f + 1 < m->flows.size() ? w.tape[f + 1].xpre : w.X;
-      if (flow_backward(m, w, m->flows[f], t->flows[f], w.tape[f], Xpost, B, T >> (i + 1), grads, st)) return 1;
+      if (flow_backward(m, w, m->flows[f], t->flows[f], w.tape[f], Xpost, B, T >> (i + 1), grads, (int)(f & 1), st)) return 1;
     }
+  if (dual_stream()) {   // join: the conditioning gradient and all weight gradients are complete
+    cudaEvent_t e = t->next_event();
+    FWN_CUDA(cudaEventRecord(e, t->side));
+    FWN_CUDA(cudaStreamWaitEvent(st, e, 0));
+  }
   // ---- upsampler
   {
     int Tm = T / m->hop;
