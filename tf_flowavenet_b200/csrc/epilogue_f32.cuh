@@ -114,6 +114,17 @@ struct Epilogue {
       const float* a0 = (e.in0 && !pre) ? reinterpret_cast<const float*>(e.in0) + row * e.ld : nullptr;
       const float* mk = e.in1 ? reinterpret_cast<const float*>(e.in1) + row * e.ld : nullptr;
       float v[4];
+      const bool vec = col + 3 < g.N && (e.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(y + col) & 15) == 0;
+      float mv[4] = {1.f, 1.f, 1.f, 1.f};
+      if (mk) {   // one 16-byte load per row instead of four 4-byte ones: row-per-thread accesses cost a cache line each
+        if (vec && (reinterpret_cast<uintptr_t>(mk + col) & 15) == 0) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(mk + col));
+          mv[0] = t4.x; mv[1] = t4.y; mv[2] = t4.z; mv[3] = t4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (col + j < g.N) mv[j] = __ldg(mk + col + j);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = col + j;
@@ -123,10 +134,10 @@ struct Epilogue {
           if (pre) v[j] += pre[j];
           else if (a0) v[j] += a0[n];
           v[j] *= e.alpha;
-          if (mk && !(__ldg(mk + n) > 0.f)) v[j] = 0.f;
+          if (!(mv[j] > 0.f)) v[j] = 0.f;
         }
       }
-      if (col + 3 < g.N && (e.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(y + col) & 15) == 0) {
+      if (vec) {
         *reinterpret_cast<float4*>(y + col) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
