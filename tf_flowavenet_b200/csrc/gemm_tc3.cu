@@ -36,6 +36,7 @@ constexpr int ABF_BYTES = NPL * A_BYTES;           // three bf16 operand tiles =
 constexpr int CONV_WARPS = 8, EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * CONV_WARPS + 32 * EPI_WARPS;
 constexpr int NTERMS = 6;
+constexpr int EPI_STG_BYTES = EPI_WARPS * 32 * 16 * 4;   // per epilogue warp: a [32 rows x 16 cols] fp32 transpose tile (16 KB in all)
 
 template <int BN>
 struct Cfg3 {
@@ -43,7 +44,7 @@ struct Cfg3 {
   static constexpr int W_BYTES = NPL * WPL_BYTES;
   static constexpr int STAGE_BYTES = A32_BYTES + W_BYTES;  // 80 KB (BN 128) / 56 KB (BN 64)
   static constexpr int NACC = 4;                           // TMEM accumulator stages
-  static constexpr size_t SMEM = 1024 + (size_t)NST * STAGE_BYTES + ABF_BYTES + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)NST * STAGE_BYTES + ABF_BYTES + EPI_STG_BYTES + 256;
 };
 
 struct alignas(64) Tc3Args {
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* abf_base = smem + (size_t)NST * C::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(abf_base + ABF_BYTES);
+  uint8_t* epi_stg = abf_base + ABF_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stg + EPI_STG_BYTES);
   uint64_t* empty_bar = full_bar + NST;
   uint64_t* conv_full = empty_bar + NST;
   uint64_t* conv_empty = conv_full + 1;
@@ -195,18 +197,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
     }
   } else {
     // ===================== epilogue: two groups of four warps alternate tiles =====================
+    // tcgen05.ld hands every thread one ROW of the accumulator; touching global memory row-per-thread costs a cache line per lane
+    // and instruction.  Each warp therefore transposes 16-column slabs through a private swizzled shared-memory tile, after which
+    // a lane owns 4 consecutive columns of 8 different rows per step: 64 contiguous bytes per row, 8 rows per memory instruction.
     const int lg = warp & 3;
-    const int grp = (warp - (2 + CONV_WARPS)) >> 2;
-    const int r = lg * 32 + lane;
+    const int ew = warp - (2 + CONV_WARPS);
+    const int grp = ew >> 2;
+    const uint32_t stg = smem_u32(epi_stg) + (uint32_t)ew * (32 * 16 * 4);
+    const uint32_t wsw = ((uint32_t)lane >> 1) & 3;                       // write side: my row = lane
+    const int rsub = lane >> 2, c4 = lane & 3;                           // read side: row 8k + rsub, column chunk c4
     double ls_sum = 0.0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
       const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
       const int ub = m_tile / a.tiles_per_utt;
-      const int t = (m_tile - ub * a.tiles_per_utt) * BM + r;
-      const bool row_ok = t < g.Ti;
-      const int64_t row = (int64_t)ub * g.Ti + t;
+      const int t_warp = (m_tile - ub * a.tiles_per_utt) * BM + lg * 32;  // first row of this warp's 32-row slab
       const int as = it % NACC;
       mbar_wait(tmem_full + as, (uint32_t)(it / NACC) & 1);
       tcgen05_fence_after();
@@ -222,22 +228,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty + as);
         }
-        if (row_ok) {
-          float pre[32];
-          if (EPI == EPI_LINEAR) {   // all addends of this batch first (see Epilogue::prefetch)
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const int col = n_tile * BN + cc + q;
-              if (col < g.N) Epilogue<EPI>::prefetch(g, row, col, pre + q);
-            }
+        for (int hb = 0; hb < 2; ++hb) {
+          __syncwarp();        // the previous slab has been read
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(stg + (uint32_t)lane * 64 + ((((uint32_t)q) ^ wsw) << 4),
+                   make_uint4(v[16 * hb + 4 * q], v[16 * hb + 4 * q + 1], v[16 * hb + 4 * q + 2], v[16 * hb + 4 * q + 3]));
+          __syncwarp();
+          const int col = n_tile * BN + cc + 16 * hb + 4 * c4;
+          float acc[4][4], pre[4][4];
+          bool ok[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rl = 8 * k + rsub;
+            const uint4 u = lds128(stg + (uint32_t)rl * 64 + ((((uint32_t)c4) ^ (((uint32_t)rl >> 1) & 3)) << 4));
+            acc[k][0] = __uint_as_float(u.x); acc[k][1] = __uint_as_float(u.y); acc[k][2] = __uint_as_float(u.z); acc[k][3] = __uint_as_float(u.w);
+            ok[k] = (t_warp + rl < g.Ti) && col < g.N;
+          }
+          if (EPI == EPI_LINEAR) {   // all addends first (see Epilogue::prefetch)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (ok[k]) Epilogue<EPI>::prefetch(g, (int64_t)ub * g.Ti + t_warp + 8 * k + rsub, col, pre[k]);
           }
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const int col = n_tile * BN + cc + q;
-            if (col < g.N) {
-              const float acc[4] = {__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])};
-              Epilogue<EPI>::apply(g, row, t, col, acc, ls_sum, (EPI == EPI_LINEAR && g.e.in0) ? pre + q : nullptr);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int tt = t_warp + 8 * k + rsub;
+            if (ok[k]) Epilogue<EPI>::apply(g, (int64_t)ub * g.Ti + tt, tt, col, acc[k], ls_sum, (EPI == EPI_LINEAR && g.e.in0) ? pre[k] : nullptr);
           }
         }
       }
