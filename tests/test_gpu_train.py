@@ -173,3 +173,19 @@ def test_two_stream_backward_equals_single_stream_at_full_depth():
     assert float((dual_a - single).abs().max()) < 1e-4 * scale
     assert float((dual_b - dual_a).abs().max()) < 1e-4 * scale
     assert abs(float(dual_a.double().norm()) - float(single.double().norm())) < 1e-5 * float(single.double().norm())
+
+
+@pytest.mark.parametrize("B,n_frames", [(1, 160), (3, 100)])
+def test_gradients_match_oracle_multi_tile(B, n_frames):
+    """Rows spanning several (partial) 128-row tiles and 64-step wgrad chunks, several utterances, and both conditioning paths:
+    T_i = 320/200 in block 0 (projection inside the gate GEMM) and 160/100 in block 1 (projection computed ahead on the side stream)."""
+    import tf_flowavenet_b200.train as T
+    hp = O.HP(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=(2, 2))
+    params = O.synthetic_params(hp, seed=21, dtype=torch.float64)
+    x, c = O.synthetic_inputs(hp, B, n_frames, 22, "x")
+    params = O.ddi_init(params, hp, x, c, torch.float64)
+    tr = T.Trainer(make_model(hp, params))
+    log_p, logdet = tr.loss_and_grads(x.float().cuda(), c.float().cuda())
+    loss, _, _, ref = TO.loss_and_grads(params, hp, x, c)
+    assert abs(float(-(log_p + logdet)) - loss) < 1e-4 * max(1.0, abs(loss))
+    check_grads(tr.gradients(), ref)

@@ -17,9 +17,10 @@ struct Epilogue {
   __device__ static __forceinline__ void prefetch(const GemmArgs& g, int64_t row, int col, float pre[4]) {
     const EpiArgs& e = g.e;
     pre[0] = pre[1] = pre[2] = pre[3] = 0.f;
-    if (EPI != EPI_LINEAR || !e.in0) return;
-    const float* a0 = reinterpret_cast<const float*>(e.in0) + row * e.ld + col;
-    if (col + 3 < g.N && (e.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a0) & 15) == 0) {
+    if ((EPI != EPI_LINEAR && EPI != EPI_GATE) || !e.in0) return;
+    const int64_t ld = EPI == EPI_GATE ? 2 * e.F : e.ld;
+    const float* a0 = reinterpret_cast<const float*>(e.in0) + row * ld + col;
+    if (col + 3 < g.N && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a0) & 15) == 0) {
       const float4 v = *reinterpret_cast<const float4*>(a0);
       pre[0] = v.x; pre[1] = v.y; pre[2] = v.z; pre[3] = v.w;
     } else {
@@ -55,6 +56,12 @@ struct Epilogue {
       if (col + 3 < g.N) {
         float f0 = acc[0] + __ldg(e.bias + col), g0 = acc[1] + __ldg(e.bias + col + 1);
         float f1 = acc[2] + __ldg(e.bias + col + 2), g1 = acc[3] + __ldg(e.bias + col + 3);
+        if (pre) {    // training, deep blocks: the conditioning projection was computed ahead (it does not depend on the flow state)
+          f0 += pre[0]; g0 += pre[1]; f1 += pre[2]; g1 += pre[3];
+        } else if (e.in0) {   // (in0 may alias out1: batch callers prefetch, see above)
+          const float4 y = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.in0) + row * (2 * e.F) + col);
+          f0 += y.x; g0 += y.y; f1 += y.z; g1 += y.w;
+        }
         float2 v = make_float2(tanhf(f0) * sigmoidf_acc(g0), tanhf(f1) * sigmoidf_acc(g1));
         *reinterpret_cast<float2*>(o + col / 2) = v;
         if (e.out1)  // training: keep the pre-activations for the backward pass

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
             acc[k][0] = __uint_as_float(u.x); acc[k][1] = __uint_as_float(u.y); acc[k][2] = __uint_as_float(u.z); acc[k][3] = __uint_as_float(u.w);
             ok[k] = (t_warp + rl < g.Ti) && col < g.N;
           }
-          if (EPI == EPI_LINEAR) {   // all addends first (see Epilogue::prefetch)
+          if (EPI == EPI_LINEAR || EPI == EPI_GATE) {   // all addends first (see Epilogue::prefetch)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (ok[k]) Epilogue<EPI>::prefetch(g, (int64_t)ub * g.Ti + t_warp + 8 * k + rsub, col, pre[k]);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int tt = t_warp + 8 * k + rsub;
-            if (ok[k]) Epilogue<EPI>::apply(g, (int64_t)ub * g.Ti + tt, tt, col, acc[k], ls_sum, (EPI == EPI_LINEAR && g.e.in0) ? pre[k] : nullptr);
+            if (ok[k]) Epilogue<EPI>::apply(g, (int64_t)ub * g.Ti + tt, tt, col, acc[k], ls_sum, ((EPI == EPI_LINEAR || EPI == EPI_GATE) && g.e.in0) ? pre[k] : nullptr);
           }
         }
       }

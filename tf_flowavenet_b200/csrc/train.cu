@@ -45,6 +45,7 @@ struct TrainState {
   std::vector<cudaEvent_t> ev;
   size_t ev_next = 0;
   cudaEvent_t set_done[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> cond_ready;   // per block: the conditioning projections of its flows are in the tape
   cudaEvent_t next_event() {
     if (ev.empty()) {
       ev.resize(64);
@@ -64,6 +65,7 @@ void train_free(Model* m) {
   cudaFree(t->norm); cudaFree(t->up_dw);
   for (auto e : t->ev) cudaEventDestroy(e);
   for (auto e : t->set_done) if (e) cudaEventDestroy(e);
+  for (auto e : t->cond_ready) cudaEventDestroy(e);
   if (t->side) cudaStreamDestroy(t->side);
   delete t;
   m->train = nullptr;
@@ -195,6 +197,8 @@ static int train_build(Model* m) {
   FWN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = numerically greatest = lowest priority
   FWN_CUDA(cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, lo));
   for (auto& e : t->set_done) FWN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  t->cond_ready.resize(c.n_block);
+  for (auto& e : t->cond_ready) FWN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
 
@@ -310,6 +314,27 @@ static bool wgrad_on_tensor_cores() {
 }
 static inline int shift_of(const fwn_config& c, int k, int d) { return c.causal ? (k - 2) * d : (k - 1) * d; }
 
+// Deep blocks (few rows per utterance, K_c in the thousands): the conditioning projections c_a . W_c of every (flow, layer) do not
+// depend on the flow state, so they are computed ahead of the dependent chain -- on the side stream, over a flat row axis (full
+// 128-row tiles instead of one mostly empty tile per utterance) -- straight into the pre-activation tape; the gate GEMM then
+// reduces over the 768 conv inputs only and adds the projection in its epilogue.
+static bool cond_ahead(int Ti, const FlowPack& fp) { return Ti <= 256 && (fp.Kc & 3) == 0 && fp.w3[GEMM_GATE0].p != nullptr; }
+static int cond_forward(Model* m, const TrainWs& w, const FlowPack& fp, const Tape& tp, int B, int Ti, cudaStream_t st) {
+  const int F = m->cfg.filter_size, L = m->cfg.n_layer;
+  const float* cond = fp.cond_half == 0 ? w.cA : w.cB;
+  for (int n = 0; n < L; ++n) {
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    g.seg[0] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
+    g.nseg = 1; g.N = 2 * F;
+    g.e.out0 = tp.fg[n]; g.e.ld = 2 * F; g.e.alpha = 1.f; g.e.F = F;
+    m->launches++;
+    FWN_CHECK(fp.w3[GEMM_GATE0 + n].p && tc3_supported(g), "internal: conditioning projection not supported by the split engine");
+    if (tc3_gemm(g, EPI_LINEAR, fp.w3[GEMM_GATE0 + n].p, fp.w3[GEMM_GATE0 + n].Kpad, fp.w3[GEMM_GATE0 + n].Npad, m->cur_terms, st)) return 1;
+  }
+  return 0;
+}
+
 static int flow_forward(Model* m, const TrainWs& w, const FlowPack& fp, const Tape& tp, int B, int Ti, cudaStream_t st) {
   const fwn_config& c = m->cfg;
   const int F = c.filter_size, L = c.n_layer, nq = fp.nq, nq4 = ceil4(nq);
@@ -333,9 +358,10 @@ static int flow_forward(Model* m, const TrainWs& w, const FlowPack& fp, const Ta
     g.B = B; g.Ti = Ti;
     for (int k = 0; k < 3; ++k) g.seg[k] = Seg{tp.h[n], F, shift_of(c, k, d), F, k * F};
     g.seg[3] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
-    g.nseg = 4;
+    g.nseg = cond_ahead(Ti, fp) ? 3 : 4;
     g.W = fp.gate_w[n]; g.ldw = fp.gate_ld; g.N = 2 * F;
     g.e.bias = fp.gate_b[n]; g.e.out0 = tp.o[n]; g.e.out1 = tp.fg[n]; g.e.F = F;
+    if (cond_ahead(Ti, fp)) g.e.in0 = tp.fg[n];   // cond_forward left the projection there
     if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
     const bool last = n == L - 1;
     GemmArgs r = {};
@@ -538,11 +564,30 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   Workspace iw = {};
   iw.up[0] = w.up0; iw.cA = w.cA; iw.cB = w.cB;
   if (run_upsample(m, iw, cmel, B, T, st)) return 1;
-  for (int i = 0; i < c.n_block; ++i)
-    for (int j = 0; j < c.n_flow; ++j) {
-      const size_t f = (size_t)i * c.n_flow + j;
-      if (flow_forward(m, w, m->flows[f], w.tape[f], B, T >> (i + 1), st)) return 1;
+  {
+    const bool dual = dual_stream();
+    cudaStream_t s1 = dual ? t->side : st;
+    if (dual) {   // the side stream sees the upsampled conditioning
+      cudaEvent_t e = t->next_event();
+      FWN_CUDA(cudaEventRecord(e, st));
+      FWN_CUDA(cudaStreamWaitEvent(s1, e, 0));
     }
+    for (int i = 0; i < c.n_block; ++i) {   // conditioning projections of the deep blocks, ahead of the chain
+      if (!cond_ahead(T >> (i + 1), m->flows[(size_t)i * c.n_flow])) continue;
+      for (int j = 0; j < c.n_flow; ++j) {
+        const size_t f = (size_t)i * c.n_flow + j;
+        if (cond_forward(m, w, m->flows[f], w.tape[f], B, T >> (i + 1), s1)) return 1;
+      }
+      if (dual) FWN_CUDA(cudaEventRecord(t->cond_ready[i], s1));
+    }
+    for (int i = 0; i < c.n_block; ++i) {
+      if (dual && cond_ahead(T >> (i + 1), m->flows[(size_t)i * c.n_flow])) FWN_CUDA(cudaStreamWaitEvent(st, t->cond_ready[i], 0));
+      for (int j = 0; j < c.n_flow; ++j) {
+        const size_t f = (size_t)i * c.n_flow + j;
+        if (flow_forward(m, w, m->flows[f], w.tape[f], B, T >> (i + 1), st)) return 1;
+      }
+    }
+  }
   if (sumsq(w.X, w.sums + 1, (int64_t)BT, st)) return 1;
   if (finish_forward(w.sums, m->d_an_logdet, logp_out, logdet_out, (double)BT, st)) return 1;
   // ---- backward
