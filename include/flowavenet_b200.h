@@ -123,7 +123,8 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
                         int64_t step, void* stream);
 /* fp32 models run their GEMMs on the tensor cores as sums of bf16 x bf16 products of 3-way split operands (fp32 accumulate).
  * 6 terms keep every product down to 2^-24 (fp32 accuracy: the parity mode, default for fwn_forward / fwn_reverse);
- * 3 terms (a1w1 + a1w2 + a2w1) are exact to ~2^-16 per product at half the tensor work (default for the training step). */
+ * 3 terms (a1w1 + a1w2 + a2w1) keep ~2^-16..2^-18 per product at half the tensor work (default for the training step; gradients
+ * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
 /* Device-side twin of fwn_prepack (needs fwn_train_enable): re-derive all operands from the current variables. */
 int fwn_repack(fwn_handle h, void* stream);

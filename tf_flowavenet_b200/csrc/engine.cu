@@ -37,6 +37,11 @@ int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowP
   if (m->cfg.precision == FWN_FP32) {
     const W3& w3 = fp.w3[gemm_id];
     if (w3.p && fp32_split_engine() && tc3_supported(g)) return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, m->cur_terms, st);
+    if (gemm_id == GEMM_FRONT) {   // the fp32 [3][nq][F] layout has tap k at row k*nq; Seg.koff carries the plane layout (k*front_k16)
+      GemmArgs gg = g;
+      for (int s = 0; s < gg.nseg; ++s) gg.seg[s].koff = s * fp.nq;
+      return simt_gemm(gg, kind, st);
+    }
     return simt_gemm(g, kind, st);
   }
   return tc_run(m, g, kind, gemm_id, fp, st);

@@ -103,7 +103,7 @@ static int train_build(Model* m) {
   if (upload(&t->d_folds, m->folds)) return 1;
   std::vector<FoldWork> fw;
   for (size_t i = 0; i < m->folds.size(); ++i)
-    for (int c0 = 0; c0 < m->folds[i].N; c0 += 32) fw.push_back(FoldWork{(int)i, c0});
+    for (int c0 = 0; c0 < m->folds[i].N; c0 += ((m->folds[i].N & 3) == 0 ? 128 : 32)) fw.push_back(FoldWork{(int)i, c0});   // see fold_kernel
   t->n_fwork = (int)fw.size();
   if (upload(&t->d_fwork, fw)) return 1;
 

@@ -12,92 +12,139 @@
 namespace fwn {
 
 // ---------------------------------------------------------------- fold (raw -> What) and its transpose
-// One CTA (32 columns x 8 row slices) per work item (descriptor, 32-column tile).
-__global__ void fold_kernel(const float* __restrict__ raw, float* __restrict__ what, const FoldDesc* __restrict__ descs,
-                            const FoldWork* __restrict__ work, int64_t raw_floats) {
-  __shared__ double red[8][33];
-  const FoldWork wk = work[blockIdx.x];
-  const FoldDesc d = descs[wk.desc];
+// One CTA (32 column lanes x 8 row slices) per work item (descriptor, column tile).  VEC = 4: a lane owns 4 consecutive columns
+// (16-byte accesses, 512 contiguous bytes per warp and row); VEC = 1 for operands whose row length is not a multiple of 4.
+template <int VEC>
+struct VecF { float v[VEC]; };
+template <int VEC>
+__device__ __forceinline__ VecF<VEC> ldv(const float* p) {
+  VecF<VEC> r;
+  if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(p); r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w; }
+  else r.v[0] = *p;
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const VecF<VEC>& r) {
+  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]);
+  else *p = r.v[0];
+}
+
+template <int VEC>
+__device__ __forceinline__ void fold_body(const float* __restrict__ raw, float* __restrict__ what, const FoldDesc& d, int col0,
+                                          int64_t raw_floats, double (*red)[8][33 * 4]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int o = wk.col0 + tx;
-  const bool ok = o < d.N;
+  const int o = col0 + tx * VEC;
+  const bool ok = o < d.N;   // N % VEC == 0, so a lane is either fully inside or fully outside
   if (d.kind == FOLD_SUM2) {
-    if (ok && ty == 0) what[raw_floats + d.d + o] = raw[d.a + o] + raw[d.b + o];
+    if (ok && ty == 0)
+      for (int j = 0; j < VEC; ++j) what[raw_floats + d.d + o + j] = raw[d.a + o + j] + raw[d.b + o + j];
     return;
   }
   const float* v = raw + d.a;
-  float sc = 0.f;
+  float sc[VEC];
   if (d.kind == FOLD_WN) {
-    double ss = 0.0;
+    double ss[VEC];
+    for (int j = 0; j < VEC; ++j) ss[j] = 0.0;
     if (ok)
-      for (int k = ty; k < d.K; k += 8) { const float x = v[(int64_t)k * d.N + o]; ss += (double)x * x; }
-    red[ty][tx] = ss;
+      for (int k = ty; k < d.K; k += 8) {
+        const VecF<VEC> x = ldv<VEC>(v + (int64_t)k * d.N + o);
+        for (int j = 0; j < VEC; ++j) ss[j] += (double)x.v[j] * x.v[j];
+      }
+    for (int j = 0; j < VEC; ++j) red[0][ty][tx * VEC + j] = ss[j];
     __syncthreads();
-    ss = 0.0;
-    for (int j = 0; j < 8; ++j) ss += red[j][tx];
-    if (ok) sc = (float)((double)raw[d.b + o] / sqrt(fmax(ss, 1e-12)));
+    for (int j = 0; j < VEC; ++j) {
+      double t = 0.0;
+      for (int q = 0; q < 8; ++q) t += red[0][q][tx * VEC + j];
+      sc[j] = ok ? (float)((double)raw[d.b + o + j] / sqrt(fmax(t, 1e-12))) : 0.f;
+    }
   } else {
-    if (ok) sc = expf(3.f * raw[d.c + o]);
-    if (ok && ty == 0) what[d.b + o] = raw[d.b + o] * sc;
+    for (int j = 0; j < VEC; ++j) sc[j] = ok ? expf(3.f * raw[d.c + o + j]) : 0.f;
+    if (ok && ty == 0)
+      for (int j = 0; j < VEC; ++j) what[d.b + o + j] = raw[d.b + o + j] * sc[j];
   }
   if (ok)
-    for (int k = ty; k < d.K; k += 8) what[d.a + (int64_t)k * d.N + o] = v[(int64_t)k * d.N + o] * sc;
+    for (int k = ty; k < d.K; k += 8) {
+      VecF<VEC> x = ldv<VEC>(v + (int64_t)k * d.N + o);
+      for (int j = 0; j < VEC; ++j) x.v[j] *= sc[j];
+      stv<VEC>(what + d.a + (int64_t)k * d.N + o, x);
+    }
+}
+__global__ void fold_kernel(const float* __restrict__ raw, float* __restrict__ what, const FoldDesc* __restrict__ descs,
+                            const FoldWork* __restrict__ work, int64_t raw_floats) {
+  __shared__ double red[2][8][33 * 4];
+  const FoldWork wk = work[blockIdx.x];
+  const FoldDesc d = descs[wk.desc];
+  if ((d.N & 3) == 0) fold_body<4>(raw, what, d, wk.col0, raw_floats, red);
+  else fold_body<1>(raw, what, d, wk.col0, raw_floats, red);
 }
 
 // In place on G (gradient w.r.t. What, raw layout + ext) -> gradient w.r.t. the raw variables.
-__global__ void unfold_kernel(const float* __restrict__ raw, float* __restrict__ G, const FoldDesc* __restrict__ descs,
-                              const FoldWork* __restrict__ work, int64_t raw_floats) {
-  __shared__ double red[2][8][33];
-  const FoldWork wk = work[blockIdx.x];
-  const FoldDesc d = descs[wk.desc];
+template <int VEC>
+__device__ __forceinline__ void unfold_body(const float* __restrict__ raw, float* __restrict__ G, const FoldDesc& d, int col0,
+                                            int64_t raw_floats, double (*red)[8][33 * 4]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int o = wk.col0 + tx;
+  const int o = col0 + tx * VEC;
   const bool ok = o < d.N;
   if (d.kind == FOLD_SUM2) {
-    if (ok && ty == 0) {
-      const float g = G[raw_floats + d.d + o];
-      G[d.a + o] = g;
-      G[d.b + o] = g;
-    }
+    if (ok && ty == 0)
+      for (int j = 0; j < VEC; ++j) {
+        const float g = G[raw_floats + d.d + o + j];
+        G[d.a + o + j] = g;
+        G[d.b + o + j] = g;
+      }
     return;
   }
   const float* v = raw + d.a;
   float* gv = G + d.a;
-  double ss = 0.0, ds = 0.0;  // sum v^2, sum G v
+  double ss[VEC], ds[VEC];  // sum v^2, sum G v
+  for (int j = 0; j < VEC; ++j) ss[j] = ds[j] = 0.0;
   if (ok)
     for (int k = ty; k < d.K; k += 8) {
-      const float x = v[(int64_t)k * d.N + o];
-      ss += (double)x * x;
-      ds += (double)gv[(int64_t)k * d.N + o] * x;
+      const VecF<VEC> x = ldv<VEC>(v + (int64_t)k * d.N + o), gg = ldv<VEC>(gv + (int64_t)k * d.N + o);
+      for (int j = 0; j < VEC; ++j) { ss[j] += (double)x.v[j] * x.v[j]; ds[j] += (double)gg.v[j] * x.v[j]; }
     }
-  red[0][ty][tx] = ss;
-  red[1][ty][tx] = ds;
+  for (int j = 0; j < VEC; ++j) { red[0][ty][tx * VEC + j] = ss[j]; red[1][ty][tx * VEC + j] = ds[j]; }
   __syncthreads();
-  ss = 0.0; ds = 0.0;
-  for (int j = 0; j < 8; ++j) { ss += red[0][j][tx]; ds += red[1][j][tx]; }
   if (!ok) return;
-  if (d.kind == FOLD_WN) {
-    // What = v g / n, n = sqrt(max(sum v^2, 1e-12)):  dg = dS / n,  dv = G g / n - v dS g / n^3   (dS = sum_k G v)
-    const double g = raw[d.b + o];
-    const bool clamped = ss <= 1e-12;
-    const double n = sqrt(fmax(ss, 1e-12));
-    const float s = (float)(g / n);
-    const float c2 = clamped ? 0.f : (float)(ds * g / (n * n * n));
-    for (int k = ty; k < d.K; k += 8) {
-      const int64_t i = (int64_t)k * d.N + o;
-      gv[i] = gv[i] * s - v[i] * c2;
-    }
-    if (ty == 0) G[d.b + o] = (float)(ds / n);
-  } else {
-    // What_w = W e, What_b = b e, e = exp(3 scale):  dW = G e, db = Gb e, dscale = 3 e (sum_k G W + Gb b)
-    const float e = expf(3.f * raw[d.c + o]);
-    for (int k = ty; k < d.K; k += 8) gv[(int64_t)k * d.N + o] *= e;
-    if (ty == 0) {
-      const float gb = G[d.b + o];
-      G[d.c + o] = (float)(3.0 * (double)e * (ds + (double)gb * raw[d.b + o]));
-      G[d.b + o] = gb * e;
+  float s[VEC], c2[VEC];
+  for (int j = 0; j < VEC; ++j) {
+    double tss = 0.0, tds = 0.0;
+    for (int q = 0; q < 8; ++q) { tss += red[0][q][tx * VEC + j]; tds += red[1][q][tx * VEC + j]; }
+    if (d.kind == FOLD_WN) {
+      // What = v g / n, n = sqrt(max(sum v^2, 1e-12)):  dg = dS / n,  dv = G g / n - v dS g / n^3   (dS = sum_k G v)
+      const double g = raw[d.b + o + j];
+      const bool clamped = tss <= 1e-12;
+      const double n = sqrt(fmax(tss, 1e-12));
+      s[j] = (float)(g / n);
+      c2[j] = clamped ? 0.f : (float)(tds * g / (n * n * n));
+      if (ty == 0) G[d.b + o + j] = (float)(tds / n);
+    } else {
+      // What_w = W e, What_b = b e, e = exp(3 scale):  dW = G e, db = Gb e, dscale = 3 e (sum_k G W + Gb b)
+      const float e = expf(3.f * raw[d.c + o + j]);
+      s[j] = e;
+      c2[j] = 0.f;
+      if (ty == 0) {
+        const float gb = G[d.b + o + j];
+        G[d.c + o + j] = (float)(3.0 * (double)e * (tds + (double)gb * raw[d.b + o + j]));
+        G[d.b + o + j] = gb * e;
+      }
     }
   }
+  for (int k = ty; k < d.K; k += 8) {
+    const int64_t i = (int64_t)k * d.N + o;
+    VecF<VEC> gg = ldv<VEC>(gv + i);
+    const VecF<VEC> x = ldv<VEC>(v + i);
+    for (int j = 0; j < VEC; ++j) gg.v[j] = gg.v[j] * s[j] - x.v[j] * c2[j];
+    stv<VEC>(gv + i, gg);
+  }
+}
+__global__ void unfold_kernel(const float* __restrict__ raw, float* __restrict__ G, const FoldDesc* __restrict__ descs,
+                              const FoldWork* __restrict__ work, int64_t raw_floats) {
+  __shared__ double red[2][8][33 * 4];
+  const FoldWork wk = work[blockIdx.x];
+  const FoldDesc d = descs[wk.desc];
+  if ((d.N & 3) == 0) unfold_body<4>(raw, G, d, wk.col0, raw_floats, red);
+  else unfold_body<1>(raw, G, d, wk.col0, raw_floats, red);
 }
 
 int fold_forward(const float* raw, float* what, const FoldDesc* descs, const FoldWork* work, int nwork, int64_t raw_floats, cudaStream_t st) {
