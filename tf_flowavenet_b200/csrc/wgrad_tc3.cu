@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
       const uint32_t dst0 = smem_u32(planes) + (isA ? 0u : (uint32_t)PL_A) + (uint32_t)row * 128;
       const uint32_t sw = (uint32_t)(row & 7);
       const uint32_t stage0 = smem_u32(stage_base);
-      float bsum = 0.f;   // dY converters: running column sum = bias gradient
+      double bsum = 0.0;  // dY converters: running column sum = bias gradient (double: it runs over every row of the slab)
       int st = 0;
       uint32_t ph = 0, pf = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
             const uint32_t mm = (uint32_t)(32 * mh + m + e);
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[e]) : "r"(src + mm * 128 + ((c4 ^ (mm & 7)) << 4)));
           }
-          bsum += x[0] + x[1];
+          bsum += (double)(x[0] + x[1]);
           split3_pair(x[0], x[1], p1[m >> 1], p2[m >> 1], p3[m >> 1]);
         }
         __syncwarp();
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc3_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(conv_full);
         if (++st == NST) { st = 0; ph ^= 1; }
       }
-      if (!isA && a.dbias && blockIdx.x == 0 && n0 + row < a.N) atomicAdd(a.dbias + n0 + row, bsum);
+      if (!isA && a.dbias && blockIdx.x == 0 && n0 + row < a.N) atomicAdd(a.dbias + n0 + row, (float)bsum);
     } else {
       // ===================== epilogue: TMEM -> shared (transpose) -> coalesced fp32 atomics =====================
       const int lg = warp & 3;

@@ -28,7 +28,7 @@ def learning_rate(global_step):
 class Trainer:
     """One tower.  `group`: torch.distributed process group over which tower gradients are averaged (None = single tower)."""
 
-    def __init__(self, model, group=None, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8, scale=1.0, split_terms=3):
+    def __init__(self, model, group=None, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8, scale=1.0, split_terms=6):
         if model._precision != _lib.FWN_FP32:
             raise ValueError("training runs on the fp32 engines: use hparams.dtype='float32'")
         self.model, self.group = model, group
