@@ -102,8 +102,13 @@ static int train_build(Model* m) {
   FWN_CUDA(cudaMalloc(&t->gwall, (size_t)m->wall_floats * 4));
   if (upload(&t->d_folds, m->folds)) return 1;
   std::vector<FoldWork> fw;
-  for (size_t i = 0; i < m->folds.size(); ++i)
-    for (int c0 = 0; c0 < m->folds[i].N; c0 += ((m->folds[i].N & 3) == 0 ? 128 : 32)) fw.push_back(FoldWork{(int)i, c0});   // see fold_kernel
+  for (size_t i = 0; i < m->folds.size(); ++i) {
+    // wide (16-byte) tiles for the many K <= 768 operands; the few long ones (conditioning convs of the deep blocks, K up to 5120)
+    // keep 32-column tiles so that their CTAs do not become the tail of the launch
+    const int vec = ((m->folds[i].N & 3) == 0 && m->folds[i].K <= 1024) ? 1 : 0;
+    for (int c0 = 0; c0 < m->folds[i].N; c0 += vec ? 128 : 32) fw.push_back(FoldWork{(int)i, c0, vec});
+  }
+  std::stable_sort(fw.begin(), fw.end(), [&](const FoldWork& x, const FoldWork& y) { return m->folds[x.desc].K > m->folds[y.desc].K; });   // longest first
   t->n_fwork = (int)fw.size();
   if (upload(&t->d_fwork, fw)) return 1;
 

@@ -6,7 +6,7 @@
 
 namespace fwn {
 
-struct FoldWork { int desc; int col0; };
+struct FoldWork { int desc; int col0; int vec; };   // vec: 128-column tile with 16-byte accesses, else 32-column tile
 
 // one fp32 operand (or a K range of one) -> bf16x3 planes:  dst[p][n][k0 + k] = split_p(src[k sk + n sn])
 struct PlaneDesc {

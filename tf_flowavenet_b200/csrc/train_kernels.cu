@@ -74,7 +74,7 @@ __global__ void fold_kernel(const float* __restrict__ raw, float* __restrict__ w
   __shared__ double red[2][8][33 * 4];
   const FoldWork wk = work[blockIdx.x];
   const FoldDesc d = descs[wk.desc];
-  if ((d.N & 3) == 0) fold_body<4>(raw, what, d, wk.col0, raw_floats, red);
+  if (wk.vec) fold_body<4>(raw, what, d, wk.col0, raw_floats, red);
   else fold_body<1>(raw, what, d, wk.col0, raw_floats, red);
 }
 
@@ -143,7 +143,7 @@ __global__ void unfold_kernel(const float* __restrict__ raw, float* __restrict__
   __shared__ double red[2][8][33 * 4];
   const FoldWork wk = work[blockIdx.x];
   const FoldDesc d = descs[wk.desc];
-  if ((d.N & 3) == 0) unfold_body<4>(raw, G, d, wk.col0, raw_floats, red);
+  if (wk.vec) unfold_body<4>(raw, G, d, wk.col0, raw_floats, red);
   else unfold_body<1>(raw, G, d, wk.col0, raw_floats, red);
 }
 
