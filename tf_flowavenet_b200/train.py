@@ -25,6 +25,18 @@ def learning_rate(global_step):
     return lr
 
 
+def average_flat_gradients(flat, group=None):
+    """utils.average_gradients (utils.py:34-60) for towers = processes: in-place mean of the flat gradient vector over `group`
+    (one all-reduce; NCCL over NVLink on GPUs, gloo in the CPU tests).  No-op without an initialised process group."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return flat
+    ws = torch.distributed.get_world_size(group)
+    if ws > 1:
+        torch.distributed.all_reduce(flat, group=group)
+        flat.mul_(1.0 / ws)
+    return flat
+
+
 class Trainer:
     """One tower.  `group`: torch.distributed process group over which tower gradients are averaged (None = single tower)."""
 
@@ -73,12 +85,7 @@ class Trainer:
 
     def average_gradients(self):
         """utils.py:34-60 across towers = processes."""
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            ws = torch.distributed.get_world_size(self.group)
-            if ws > 1:
-                flat = self.grads[:self._np]
-                torch.distributed.all_reduce(flat, group=self.group)
-                flat.mul_(1.0 / ws)
+        average_flat_gradients(self.grads[:self._np], self.group)
 
     def apply_gradients(self):
         """clip_by_global_norm + Adam (train.py:76-81); returns the (pre-clip) global norm as a device scalar."""
