@@ -211,3 +211,31 @@ def test_gradients_match_oracle_multi_tile(B, n_frames):
             check_grads_global(tr.gradients(), ref, 1e-3, 1e-3)
         else:
             check_grads_global(tr.gradients(), ref, 5e-3, 5e-3)
+
+
+def test_dataset_feeds_trainer(tmp_path):
+    """dataset.py -> train.py wiring: TFRecord clips -> hop-aligned crops -> pinned per-tower batches -> train_step (with speaker ids)."""
+    import tf_flowavenet_b200 as P
+    import tf_flowavenet_b200.train as T
+    from tf_flowavenet_b200 import dataset as D
+    hp = P.HParams(n_block=2, n_flow=2, n_layer=2, num_mels=8, upsample_scales=[2, 2], hop_size=4, max_time_steps=64, batch_size=2,
+                   gin_channels=4, n_speakers=3, dtype="float32")
+    path = str(tmp_path / "train.tfrecord")
+    rng = np.random.default_rng(0)
+    with D.TFRecordWriter(path) as w:
+        for i in range(5):
+            frames = int(rng.integers(10, 40))
+            audio = (0.5 * np.sin(np.arange(frames * 4) * 0.1 * (i + 1)) + 0.05 * rng.standard_normal(frames * 4)).astype(np.float32)
+            audio, mel = D.adjust_time_resolution(audio, rng.random((frames, 8)).astype(np.float32), hp)
+            w.write(D.make_example(audio, mel, i % 3))
+    net = P.FloWaveNet(hp, variables=P.VariableStore())
+    net.init_variables(seed=1, zero_init_coupling=False)
+    tr = T.Trainer(net)
+    it = iter(D.Dataset(path, hp, num_towers=1, seed=2))
+    losses = []
+    for step in range(4):
+        mel, audio, spk = next(it)[0]
+        assert tuple(audio.shape) == (2, 64, 1) and tuple(mel.shape) == (2, 16, 8)
+        info = tr.train_step(audio.cuda(non_blocking=True), mel.cuda(non_blocking=True), spk.cuda(non_blocking=True), init=(step == 0))
+        losses.append(float(info["loss"]))
+    assert all(np.isfinite(losses)) and tr.global_step == 4
