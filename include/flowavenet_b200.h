@@ -126,6 +126,11 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
  * 3 terms (a1w1 + a1w2 + a2w1) keep ~2^-16..2^-18 per product at half the tensor work (default for the training step; gradients
  * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
+/* Checkpoint / resume of a training run (train.py:190,199-210: tf.train.Saver over the variables and the Adam slots).
+ * which: 0 = the flat variable vector, 1 = Adam first moments, 2 = Adam second moments; numel = fwn_param_floats(h).
+ * Setting the variables re-derives every packed operand on the device.  The step counter lives with the caller. */
+int fwn_get_train_state(fwn_handle h, int which, float* dev_dst, int64_t numel, void* stream);
+int fwn_set_train_state(fwn_handle h, int which, const float* dev_src, int64_t numel, void* stream);
 /* Device-side twin of fwn_prepack (needs fwn_train_enable): re-derive all operands from the current variables. */
 int fwn_repack(fwn_handle h, void* stream);
 

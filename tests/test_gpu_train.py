@@ -239,3 +239,27 @@ def test_dataset_feeds_trainer(tmp_path):
         info = tr.train_step(audio.cuda(non_blocking=True), mel.cuda(non_blocking=True), spk.cuda(non_blocking=True), init=(step == 0))
         losses.append(float(info["loss"]))
     assert all(np.isfinite(losses)) and tr.global_step == 4
+
+
+def test_checkpoint_resume_continues_the_same_trajectory():
+    """train.py:190,199-210: saving variables + Adam slots + step and restoring them into a fresh trainer continues bit-compatibly
+    (up to the order of fp32 atomics in the weight gradients)."""
+    import tf_flowavenet_b200.train as T
+    hp, params, fx = load("g1_b2f2l2")
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    tr = T.Trainer(make_model(hp, params))
+    for _ in range(2):
+        tr.train_step(x, c)
+    state = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in tr.state_dict().items()}
+    for _ in range(2):
+        a = tr.train_step(x, c)
+    tr2 = T.Trainer(make_model(hp, params))       # fresh handle, initial variables, zero moments
+    tr2.load_state_dict(state)
+    assert tr2.global_step == 2
+    for _ in range(2):
+        b = tr2.train_step(x, c)
+    assert abs(float(a["loss"]) - float(b["loss"])) < 1e-5 * max(1.0, abs(float(a["loss"])))
+    assert b["learning_rate"] == a["learning_rate"] and b["global_step"] == a["global_step"] == 4
+    va, vb = tr.state_dict(), tr2.state_dict()
+    for k in ("variables", "adam_m", "adam_v"):
+        assert float((va[k] - vb[k]).abs().max()) <= 1e-5 * max(float(va[k].abs().max()), 1e-12), k

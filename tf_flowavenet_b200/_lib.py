@@ -48,6 +48,8 @@ SIGNATURES = {
     "fwn_grad_global_norm": (_i, [_p, _fp, _fp, _p]),
     "fwn_apply_gradients": (_i, [_p, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _l, _p]),
     "fwn_set_split_terms": (_i, [_p, _i, _i]),
+    "fwn_get_train_state": (_i, [_p, _i, _fp, _l, _p]),
+    "fwn_set_train_state": (_i, [_p, _i, _fp, _l, _p]),
     "fwn_repack": (_i, [_p, _p]),
     "fwn_last_launches": (_l, [_p]),
     "fwn_profile_enable": (_i, [_p, _i]),

@@ -192,6 +192,14 @@ int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms) {
   model_drop_graphs(h->m);   // captured launches carry the old setting
   return 0;
 }
+int fwn_get_train_state(fwn_handle h, int which, float* dev_dst, int64_t numel, void* stream) {
+  FWN_CHECK(h && dev_dst, "null argument");
+  return train_state_copy(h->m, which, dev_dst, nullptr, numel, S(stream));
+}
+int fwn_set_train_state(fwn_handle h, int which, const float* dev_src, int64_t numel, void* stream) {
+  FWN_CHECK(h && dev_src, "null argument");
+  return train_state_copy(h->m, which, nullptr, dev_src, numel, S(stream));
+}
 int fwn_repack(fwn_handle h, void* stream) {
   FWN_CHECK(h, "null handle");
   return train_repack(h->m, S(stream));

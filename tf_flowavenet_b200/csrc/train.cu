@@ -648,6 +648,21 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   return 0;
 }
 
+// Checkpoint / resume (train.py:190,199-210: tf.train.Saver over tf.global_variables() = variables + Adam slots + global_step).
+// which: 0 = the flat variable vector, 1 = Adam first moments, 2 = Adam second moments; same flat layout for all three.
+int train_state_copy(Model* m, int which, float* dst, const float* src, int64_t numel, cudaStream_t st) {
+  FWN_CHECK(m && m->train, "training not enabled");
+  FWN_CHECK(which >= 0 && which <= 2, "unknown state vector %d", which);
+  FWN_CHECK(numel == m->raw_floats, "state vector has %lld floats, expected %lld", (long long)numel, (long long)m->raw_floats);
+  float* mine = which == 0 ? m->raw : which == 1 ? m->train->adam_m : m->train->adam_v;
+  if (dst) FWN_CUDA(cudaMemcpyAsync(dst, mine, (size_t)numel * 4, cudaMemcpyDeviceToDevice, st));
+  if (src) {
+    FWN_CUDA(cudaMemcpyAsync(mine, src, (size_t)numel * 4, cudaMemcpyDeviceToDevice, st));
+    if (which == 0) return train_repack(m, st);   // every derived operand follows the variables
+  }
+  return 0;
+}
+
 int train_grad_norm(Model* m, const float* grads, float* norm_out, cudaStream_t st) {
   FWN_CHECK(m && m->train, "training not enabled");
   return grad_global_norm(grads, m->raw_floats, m->train->scratch, norm_out, st);

@@ -82,5 +82,6 @@ int train_loss_and_grads(Model* m, const float* x, const float* c, const int32_t
 int train_grad_norm(Model* m, const float* grads, float* norm_out, cudaStream_t st);
 int train_apply(Model* m, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm, int64_t step, cudaStream_t st);
 int train_repack(Model* m, cudaStream_t st);
+int train_state_copy(Model* m, int which, float* dst, const float* src, int64_t numel, cudaStream_t st);
 
 }  // namespace fwn

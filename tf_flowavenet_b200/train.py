@@ -109,6 +109,26 @@ class Trainer:
         return {"log_p": log_p, "logdet": logdet, "loss": -(log_p + logdet), "grad_global_norm": norm, "learning_rate": lr,
                 "global_step": self.global_step}
 
+    def state_dict(self):
+        """What the reference's Saver writes (train.py:190: variables, Adam slots, global_step), as flat device tensors."""
+        m, L = self.model, _lib.lib()
+        out = {"global_step": self.global_step}
+        with torch.cuda.device(m._device):
+            for which, key in enumerate(("variables", "adam_m", "adam_v")):
+                t = torch.empty(self._np, dtype=torch.float32, device=m._device)
+                _lib.check(L.fwn_get_train_state(m._h, which, _lib.ptr(t), t.numel(), _lib.stream_ptr()))
+                out[key] = t
+        return out
+
+    def load_state_dict(self, state):
+        """Resume (train.py:199-210): variables (every packed operand is re-derived on the device), Adam slots, step counter."""
+        m, L = self.model, _lib.lib()
+        with torch.cuda.device(m._device):
+            for which, key in enumerate(("variables", "adam_m", "adam_v")):
+                t = state[key].to(m._device, torch.float32).contiguous()
+                _lib.check(L.fwn_set_train_state(m._h, which, _lib.ptr(t), t.numel(), _lib.stream_ptr()))
+        self.global_step = int(state["global_step"])
+
     def gradients(self):
         """{variable name -> view of the flat gradient}."""
         m, L, out = self.model, _lib.lib(), {}
