@@ -254,6 +254,11 @@ def main_train(args):
             "traffic": None, "algorithmic_flop_per_step_per_gpu": flop_step,
             "phases_ms_per_step": {"loss_and_grads": phase[0] / args.steps, "allreduce_avg": phase[1] / args.steps,
                                    "clip_adam_repack": phase[2] / args.steps}}
+    tp = os.path.join(ROOT, "profiles", "r1_c5_traffic.json")
+    if os.path.exists(tp):   # DRAM bytes of ONE ncu --set full capture of the kernel with the largest share of the step
+        tj = json.load(open(tp))
+        roof["traffic"] = tj["traffic_bytes_per_launch"]
+        roof["traffic_detail"] = tj
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "roofline": roof, "clocks": clk,
