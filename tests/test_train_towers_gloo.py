@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 from oracle import flowavenet_oracle as O
 from oracle import flowavenet_train_oracle as TO
-from tf_flowavenet_b200.train import average_flat_gradients, learning_rate
+from tf_flowavenet_b200.train import average_flat_gradients, broadcast_flat_variables, learning_rate
 
 
 def _free_port():
@@ -43,6 +43,10 @@ def _worker(rank, world, port, q):
         gathered = [torch.zeros_like(new) for _ in range(world)]
         dist.all_gather(gathered, new)
         same = all(torch.equal(gathered[0], t) for t in gathered)
+        # after the data-dependent init every tower adopts rank 0's variables
+        mine_vars = torch.full((7,), float(rank + 1))
+        broadcast_flat_variables(mine_vars)
+        same = same and bool(torch.all(mine_vars == 1.0))
         q.put((rank, err, same, norm))
     finally:
         dist.destroy_process_group()

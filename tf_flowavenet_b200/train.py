@@ -37,6 +37,15 @@ def average_flat_gradients(flat, group=None):
     return flat
 
 
+def broadcast_flat_variables(flat, src=0, group=None):
+    """Towers share ONE set of variables in the reference (tf.variable_scope reuse, train.py:51-53).  With one process per tower
+    the data-dependent ActNorm initialisation (train.py:221,229) would leave every rank with its own statistics, so rank `src`'s
+    variable vector is broadcast after it (documented deviation -- the reference's init step lets the last tower win)."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+        torch.distributed.broadcast(flat, src=src, group=group)
+    return flat
+
+
 class Trainer:
     """One tower.  `group`: torch.distributed process group over which tower gradients are averaged (None = single tower)."""
 
@@ -103,11 +112,25 @@ class Trainer:
         """One sess.run([..., train_op]) of train.py:221/229/236.  init=True is the ActNorm data-dependent initialisation step."""
         if init:
             self.model.initialize_actnorm(x, c, g)
+            self.sync_variables()
         log_p, logdet = self.loss_and_grads(x, c, g)
         self.average_gradients()
         norm, lr = self.apply_gradients()
         return {"log_p": log_p, "logdet": logdet, "loss": -(log_p + logdet), "grad_global_norm": norm, "learning_rate": lr,
                 "global_step": self.global_step}
+
+    def sync_variables(self, src=0):
+        """All towers adopt rank `src`'s variables (no-op for a single tower)."""
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        if torch.distributed.get_world_size(self.group) < 2:
+            return
+        m, L = self.model, _lib.lib()
+        with torch.cuda.device(m._device):
+            flat = torch.empty(self._np, dtype=torch.float32, device=m._device)
+            _lib.check(L.fwn_get_train_state(m._h, 0, _lib.ptr(flat), flat.numel(), _lib.stream_ptr()))
+            broadcast_flat_variables(flat, src, self.group)
+            _lib.check(L.fwn_set_train_state(m._h, 0, _lib.ptr(flat), flat.numel(), _lib.stream_ptr()))
 
     def state_dict(self):
         """What the reference's Saver writes (train.py:190: variables, Adam slots, global_step), as flat device tensors."""
