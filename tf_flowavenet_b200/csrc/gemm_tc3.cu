@@ -55,7 +55,7 @@ struct alignas(64) Tc3Args {
   CUtensorMap mapW;     // bf16 weight planes: (Kpad, Npad, 3), box (64, BN, 1)
   int shift[4], nchunk[4], last_ksteps[4], wk0[4];
   int nseg, tiles_per_utt, n_tiles;
-  int nterms;           // 6: all products down to 2^-24 (fp32 accuracy); 3: a1w1 + a1w2 + a2w1 (2^-16 per product)
+  int nterms;           // 6: all products down to 2^-24; 3: a1w1 + a1w2 + a2w1 (~2^-16 per product)
   GemmArgs g;
 };
 

@@ -83,7 +83,7 @@ struct Model {
   bool keep_map = false;            // fwn_train_enable: keep the gather map of that region
   std::vector<int32_t> host_wmap;   // [wall_floats] What index | sign << 30, -1 = constant
   TrainState* train = nullptr;
-  // bf16 split terms per fp32 product on the tensor cores: 6 = fp32 accuracy (2^-24), 3 = 2^-16 per product (fwn_set_split_terms)
+  // bf16 split terms per fp32 product on the tensor cores: 6 = every product down to 2^-24, 3 = ~2^-16 per product (fwn_set_split_terms)
   int terms_infer = 6, terms_train = 3, cur_terms = 6;
   bool packed = false, rev_ok = false;
   char* pack = nullptr;

@@ -1,4 +1,4 @@
-// Weight gradients on the tensor cores with fp32 accuracy (3-way bf16 split of BOTH operands, fp32 accumulation in TMEM):
+// Weight gradients on the tensor cores in the fp32 parity mode (3-way bf16 split of BOTH operands, fp32 accumulation in TMEM):
 //   dW[koff + k, n] += sum_{b,t} A[b, t + shift, k] * dY[b, t, n]
 // The reduction runs over time, so both operands are needed "transposed" (reduction index contiguous).  TMA brings fp32 tiles
 // [64 time steps x 128 channels] of A and dY into shared memory; eight converter warps read them COLUMN-wise (one channel per

@@ -60,7 +60,7 @@ class Trainer:
         model._sync_params()
         with torch.cuda.device(model._device):
             _lib.check(L.fwn_train_enable(model._h, _lib.stream_ptr()))
-        # split_terms: bf16 products per fp32 product in the training GEMMs.  6 = fp32 accuracy (every variable's gradient within
+        # split_terms: bf16 products per fp32 product in the training GEMMs.  6 = every product down to 2^-24 (every variable's gradient within
         # 2e-4 of a float64 reference); 3 = ~2^-16..2^-18 per product at half the tensor work (errors up to ~1e-3 of the largest
         # gradient entry on cancellation-heavy gradients; ~10x tighter than bf16).  Inference passes always use 6.
         _lib.check(L.fwn_set_split_terms(model._h, 6, int(split_terms)))
