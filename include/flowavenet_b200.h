@@ -26,8 +26,11 @@ extern "C" {
 #define FWN_ABI_VERSION 1
 
 enum fwn_precision {
-  FWN_FP32 = 0,       /* fp32 storage + fp32 CUDA-core math: the parity mode (1e-4 rel vs oracle)        */
-  FWN_MIXED_BF16 = 1  /* bf16 operands/activations, fp32 accumulate (tcgen05), fp32 flow variables x, log-det */
+  FWN_FP32 = 0,        /* fp32 storage, fp32-accurate GEMMs on tcgen05 via 3-way bf16 operand split (or CUDA cores):
+                          the parity mode (1e-4 rel vs oracle)                                                   */
+  FWN_MIXED_BF16 = 1,  /* bf16 operands/activations, fp32 accumulate (tcgen05), fp32 flow variable x and log-det  */
+  FWN_MIXED_FP16 = 2   /* fp16 operands/activations -- the reference's own mixed dtype (hparams.py:9, utils.py:3-31) --
+                          fp32 accumulate (tcgen05), fp32 flow variable x and log-det; 8x finer operand rounding than bf16 */
 };
 
 /* hparams.py:6-50 / hparams8000.py -- only the fields FloWaveNet.__init__ reads (model.py:288-314). */

@@ -33,6 +33,10 @@ CASES = {
     "g4_causal": (dict(n_block=2, n_flow=2, n_layer=2, num_mels=4, upsample_scales=(2, 2), causality=True), 1, 10, 14),
     "g5_additive": (dict(n_block=2, n_flow=2, n_layer=2, num_mels=4, upsample_scales=(2, 2), affine=False), 2, 6, 15),
     "g6_l3": (dict(n_block=1, n_flow=2, n_layer=3, num_mels=6, upsample_scales=(2,)), 1, 24, 16),
+    # full depth, 80 mels: the real K_c ladder (80 .. 10240) and variable count of hparams8000.py (5x6x2, 1 416 names) and
+    # hparams.py (8x6x2, 2 262 names, model.py:293-299) on a few frames
+    "g7_hparams8000": (dict(n_block=5, upsample_scales=(8, 12)), 1, 3, 17),
+    "g8_hparams": (dict(n_block=8, upsample_scales=(16, 16)), 1, 2, 18),
 }
 
 
@@ -73,7 +77,10 @@ def run_reference(hp, params, x, c, z_in, dtype, ddi=False):
 
 
 def main():
+    only = set(sys.argv[1:])   # optional: regenerate just the named cases
     for name, (kw, B, nf, seed) in CASES.items():
+        if only and name not in only:
+            continue
         hp = O.HP(**kw)
         params = O.synthetic_params(hp, seed=seed, dtype=torch.float64)
         x, c = O.synthetic_inputs(hp, B, nf, seed + 100, "x")

@@ -22,9 +22,15 @@ def test_oracle_matches_reference_run(case):
     np.testing.assert_allclose(c_up.numpy(), fx["c_up"], rtol=0, atol=1e-12)
 
 
-def test_variable_names_match_reference_scoping():
-    hp, params, fx = load("g1_b2f2l2")
-    assert sorted(O.param_shapes(hp)) == str(fx["names"]).split("\n")
+@pytest.mark.parametrize("case,count", [("g1_b2f2l2", None), ("g7_hparams8000", 47 * 30 + 6), ("g8_hparams", 47 * 48 + 6)])
+def test_variable_names_match_reference_scoping(case, count):
+    """Names created by the reference's own scoping code; the full-depth cases pin the variable count of the shipped
+    configurations (hparams.py: 47 per flow x 48 flows + 6 upsampler = 2 262)."""
+    hp, params, fx = load(case)
+    names = str(fx["names"]).split("\n")
+    assert sorted(O.param_shapes(hp)) == names
+    if count is not None:
+        assert len(names) == count
 
 
 def test_ddi_matches_reference_run():

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libflowavenet_b200.so")
 
-FWN_FP32, FWN_MIXED_BF16 = 0, 1
+FWN_FP32, FWN_MIXED_BF16, FWN_MIXED_FP16 = 0, 1, 2
 
 
 class FwnConfig(C.Structure):

@@ -351,7 +351,7 @@ int fwn_upsample_stage(const float* c_in, const float* kernel, const float* g, c
   Scratch sc;
   if (sc.get((size_t)2 * s * 3 * sizeof(float), S(stream))) return 1;
   if (upsample_weight_norm(kernel, g, (float*)sc.p, s, S(stream))) return 1;
-  return upsample_stage(c_in, (const float*)sc.p, bias, c_out, nullptr, B, Tm, mels, s, false, false, S(stream));
+  return upsample_stage(c_in, (const float*)sc.p, bias, c_out, nullptr, B, Tm, mels, s, false, 0, S(stream));
 }
 
 int fwn_conv1d(const float* x, const float* kernel, const float* wn_g, const float* bias, float* y, int B, int T, int Cin, int Cout,

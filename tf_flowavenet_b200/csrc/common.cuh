@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -47,6 +48,16 @@ inline cudaError_t launch_status() {
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// FWN_PDL=0 launches the tensor-core GEMM chain without programmatic dependent launch (diagnostics / A-B timing)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int num_sms();
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -81,5 +92,20 @@ template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+// two floats -> one 32-bit word of the 16-bit storage type (low half = first element)
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// precision modes whose activations / GEMM operands are 16-bit (bf16 or fp16) on the tcgen05 engine
+inline bool is_mixed(int precision) { return precision == 1 || precision == 2; }   // FWN_MIXED_BF16, FWN_MIXED_FP16
 
 }  // namespace fwn

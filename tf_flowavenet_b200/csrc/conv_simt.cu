@@ -289,8 +289,9 @@ int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st) {
 
 // Gather the pass-through half of the flow variable, apply ActNorm (forward direction) and cast to bf16: the A operand of the
 // tensor-core front conv.  One thread per (row, 8 output columns): X rows are contiguous so a warp reads whole rows.
+template <typename T16>
 __global__ void front_pack_kernel(const float* __restrict__ X, int Cx, int nq, int kq, const int* __restrict__ off2log,
-                                  const float* __restrict__ an_b, const float* __restrict__ an_s, __nv_bfloat16* __restrict__ A0, int64_t rows) {
+                                  const float* __restrict__ an_b, const float* __restrict__ an_s, T16* __restrict__ A0, int64_t rows) {
   const int64_t n = rows * Cx;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / Cx;
@@ -299,16 +300,17 @@ __global__ void front_pack_kernel(const float* __restrict__ X, int Cx, int nq, i
     if (q >= nq) continue;
     float v = __ldg(X + i);
     if (an_b) v = (v + __ldg(an_b + o)) * __ldg(an_s + o);
-    A0[row * kq + q] = __float2bfloat16_rn(v);
+    A0[row * kq + q] = from_f<T16>(v);
   }
 }
 int front_pack(const float* X, int Cx, int nq, int kq, const int* off2log, const float* an_b, const float* an_s, void* A0, int64_t rows,
-               cudaStream_t st) {
+               bool fp16, cudaStream_t st) {
   if (rows <= 0) return 0;
   if (kq != nq) FWN_CUDA(cudaMemsetAsync(A0, 0, (size_t)rows * kq * 2, st));  // padding columns must be finite (they meet zero weights)
   const int64_t n = rows * Cx;
   int grid = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)num_sms() * 16);
-  front_pack_kernel<<<grid, 256, 0, st>>>(X, Cx, nq, kq, off2log, an_b, an_s, reinterpret_cast<__nv_bfloat16*>(A0), rows);
+  if (fp16) front_pack_kernel<__half><<<grid, 256, 0, st>>>(X, Cx, nq, kq, off2log, an_b, an_s, reinterpret_cast<__half*>(A0), rows);
+  else front_pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(X, Cx, nq, kq, off2log, an_b, an_s, reinterpret_cast<__nv_bfloat16*>(A0), rows);
   FWN_LAUNCH_CHECK();
   return 0;
 }

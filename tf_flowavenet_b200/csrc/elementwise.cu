@@ -500,11 +500,9 @@ __global__ void upsample_warp_kernel(const float* __restrict__ in, const float* 
         }
         const int64_t bt = (int64_t)b * To + i;
         TOut* dst = SPLIT ? (pl == 0 ? out0 : out1) + bt * half + gi * 8 : out0 + bt * mels + gi * 8;
-        if (sizeof(TOut) == 2) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                                      *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+        if constexpr (sizeof(TOut) == 2) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<TOut>(acc[0], acc[1]), pack2<TOut>(acc[2], acc[3]),
+                                                      pack2<TOut>(acc[4], acc[5]), pack2<TOut>(acc[6], acc[7]));
         } else {
           reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
           reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -550,8 +548,9 @@ int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* o
   return 0;
 }
 int upsample_stage(const float* in, const float* w, const float* bias, void* out0, void* out1, int B, int Tm, int mels, int s, bool split,
-                   bool bf16, cudaStream_t st) {
-  if (bf16) return upsample_stage_t<__nv_bfloat16>(in, w, bias, (__nv_bfloat16*)out0, (__nv_bfloat16*)out1, B, Tm, mels, s, split, st);
+                   int out_kind, cudaStream_t st) {
+  if (out_kind == 1) return upsample_stage_t<__nv_bfloat16>(in, w, bias, (__nv_bfloat16*)out0, (__nv_bfloat16*)out1, B, Tm, mels, s, split, st);
+  if (out_kind == 2) return upsample_stage_t<__half>(in, w, bias, (__half*)out0, (__half*)out1, B, Tm, mels, s, split, st);
   return upsample_stage_t<float>(in, w, bias, (float*)out0, (float*)out1, B, Tm, mels, s, split, st);
 }
 

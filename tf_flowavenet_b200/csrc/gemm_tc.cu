@@ -40,6 +40,7 @@ struct alignas(64) TcArgs {
   int wk0[MAX_SEG];          // first W column (k) of the segment
   int nseg;
   int multicast;             // weight map has (64, BN/2) boxes and the kernel runs as cta_group::2 CTA pairs
+  int fp16;                  // operands / activations are fp16 instead of bf16 (FWN_MIXED_FP16)
   int B, Ti, tiles_per_utt, n_tiles, N;
   EpiArgs e;
 };
@@ -99,6 +100,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
                                            uint8_t* stg, bool have_in, const uint4* inp, const float* sbias, double& ls_sum) {
   using C = Cfg<EPI, BN, WS, false>;
   const EpiArgs& e = a.e;
+  const bool fp16 = a.fp16 != 0;
   const int col = n_tile * BN + c0;  // global column of v[0]
   float acc[16];
   {  // bias from shared memory (broadcast 128-bit reads): WS kernels stage their own column tile, the others all columns
@@ -116,12 +118,19 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
     // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124); 16 columns -> 8 channels = one 16-byte chunk
     uint32_t p[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // tanh(f) * sigmoid(g) = t + t*tanh(g/2) with t = tanh(f)/2 : 2 MUFU + 3 FP32 ops per output
-      const float t0 = 0.5f * tanh_fast(acc[4 * j]), t1 = 0.5f * tanh_fast(acc[4 * j + 2]);
-      const float o0 = fmaf(tanh_fast(0.5f * acc[4 * j + 1]), t0, t0);
-      const float o1 = fmaf(tanh_fast(0.5f * acc[4 * j + 3]), t1, t1);
-      p[j] = pack_bf16(o0, o1);
+    if (fp16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        p[j] = pack16(gate_accurate(acc[4 * j], acc[4 * j + 1]), gate_accurate(acc[4 * j + 2], acc[4 * j + 3]), true);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // tanh(f) * sigmoid(g) = t + t*tanh(g/2) with t = tanh(f)/2 : 2 MUFU + 3 FP32 ops per output
+        const float t0 = 0.5f * tanh_fast(acc[4 * j]), t1 = 0.5f * tanh_fast(acc[4 * j + 2]);
+        const float o0 = fmaf(tanh_fast(0.5f * acc[4 * j + 1]), t0, t0);
+        const float o1 = fmaf(tanh_fast(0.5f * acc[4 * j + 3]), t1, t1);
+        p[j] = pack_bf16(o0, o1);
+      }
     }
     sts128(smem_u32(stg) + stg_off(r, c0 / 2), make_uint4(p[0], p[1], p[2], p[3]));
   } else if (EPI == EPI_RES_SKIP) {
@@ -133,7 +142,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float lo, hi;
-        unpack_bf16(hu[j], lo, hi);
+        unpack16(hu[j], lo, hi, fp16);
         acc[2 * j] += lo;
         acc[2 * j + 1] += hi;
       }
@@ -149,7 +158,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
         lo = fmaxf(lo, 0.f);
         hi = fmaxf(hi, 0.f);
       }
-      p[j] = pack_bf16(lo, hi);
+      p[j] = pack16(lo, hi, fp16);
     }
     sts128(sbase + stg_off(r, c0), make_uint4(p[0], p[1], p[2], p[3]));
     sts128(sbase + stg_off(r, c0 + 8), make_uint4(p[4], p[5], p[6], p[7]));
@@ -159,7 +168,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
     for (int j = 0; j < 8; ++j) {
       float lo = acc[2 * j], hi = acc[2 * j + 1];
       if (e.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-      p[j] = pack_bf16(lo, hi);
+      p[j] = pack16(lo, hi, fp16);
     }
     if (C::STAGED) {
       sts128(smem_u32(stg) + stg_off(r, c0), make_uint4(p[0], p[1], p[2], p[3]));
@@ -170,10 +179,10 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
         op[0] = make_uint4(p[0], p[1], p[2], p[3]);
         op[1] = make_uint4(p[4], p[5], p[6], p[7]);
       } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out0) + row * e.ld + col;
+        uint16_t* o = reinterpret_cast<uint16_t*>(e.out0) + row * e.ld + col;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (col + j < a.N) o[j] = __float2bfloat16_rn(e.relu ? fmaxf(acc[j], 0.f) : acc[j]);
+          if (col + j < a.N) o[j] = (uint16_t)(pack16(e.relu ? fmaxf(acc[j], 0.f) : acc[j], 0.f, fp16) & 0xFFFFu);
       }
     }
   } else if (EPI == EPI_AFFINE) {
@@ -315,6 +324,8 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   if (PAIR) cluster_sync_all();  // peer barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // the next kernel of the chain may be scheduled as SMs free up (its own prologue overlaps our tail) ...
+  pdl_launch_dependents();
 
   // which input map (if any) feeds the epilogue of column tile n_tile (RES_SKIP only)
   auto input_map_of = [&](int n_tile) -> int {
@@ -338,6 +349,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
           for (int ch = 0; ch < a.nchunk[s]; ++ch, ++c)
             tma_load_2d(w_base + (size_t)c * C::B_BYTES, &a.mapB, w_full, a.wk0[s] + ch * BK, ws_n * BN);
       }
+      pdl_wait();   // ... and we touch activations only once the previous kernel of the chain has completed
       for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
         const int ub = m_tile / a.tiles_per_utt;
         const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
@@ -377,7 +389,8 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = PAIR ? (make_idesc<BN>() & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24) : make_idesc<BN>();
+    constexpr uint32_t idesc_bf16 = PAIR ? (make_idesc<BN>() & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24) : make_idesc<BN>();
+    const uint32_t idesc = a.fp16 ? (idesc_bf16 & ~IDESC_BF16_BITS) : idesc_bf16;
     int stage = 0, as = 0;
     uint32_t phase = 0, aphase = 0;
     int m_tile, n_tile;
@@ -422,6 +435,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
     const int r = lg * 32 + lane;
     double ls_sum = 0.0;
     int m_tile, n_tile;
+    pdl_wait();   // epilogue warps read / write global memory themselves (x rows, clipped stores): same rule as the producer
     for (int it = grp; tile_of(it, m_tile, n_tile); it += C::GROUPS) {
       const int as = it % C::NACC;
       const uint32_t aphase = (uint32_t)(it / C::NACC) & 1;
@@ -551,6 +565,8 @@ static EncodeFn get_encode() {
 }
 
 // activations [B, Ti, C] bf16 (row stride ld elements) -> 3-D map, box (64, 128, 1), 128B swizzle, zero OOB fill
+static bool g_map_fp16 = false;   // element type the next tensor maps are encoded with (set by tc_prepare; both are 2-byte types)
+static CUtensorMapDataType map_dtype() { return g_map_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 int make_act_map(CUtensorMap* map, const void* base, int B, int Ti, int C, int64_t ld) {
   EncodeFn enc = get_encode();
   FWN_CHECK(enc, "cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -559,7 +575,7 @@ int make_act_map(CUtensorMap* map, const void* base, int B, int Ti, int C, int64
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)Ti};
   cuuint32_t box[3] = {BK, BM, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, map_dtype(), 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations B=%d Ti=%d C=%d) failed: %d", B, Ti, C, (int)r);
   return 0;
@@ -573,7 +589,7 @@ int make_store_map(CUtensorMap* map, const void* base, int B, int Ti, int C, int
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)Ti};
   cuuint32_t box[3] = {BK, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, map_dtype(), 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store map B=%d Ti=%d C=%d) failed: %d", B, Ti, C, (int)r);
   return 0;
@@ -586,7 +602,7 @@ int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
   cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
   cuuint32_t box[2] = {BK, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, map_dtype(), 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights N=%d K=%d box=%d) failed: %d", Npad, Kpad, bn, (int)r);
   return 0;
@@ -614,23 +630,28 @@ static int launch(const TcArgs& a, cudaStream_t st) {
   } else {
     grid = std::min(num_m * a.n_tiles, num_sms());
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (PAIR) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(C::THREADS);
-    cfg.dynamicSmemBytes = C::SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    FWN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, WS, PAIR>, a));
-  } else {
-    tc_gemm_kernel<EPI, BN, WS, PAIR><<<grid, C::THREADS, C::SMEM, st>>>(a);
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl_enabled()) {   // programmatic dependent launch: see pdl_wait() in tc_ptx.cuh
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  FWN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, WS, PAIR>, a));
   FWN_LAUNCH_CHECK();
   return 0;
 }
@@ -714,6 +735,7 @@ int tc_prepare(Model* m, const Workspace& w, int B, int T, cudaStream_t st) {
   const int F = c.filter_size, L = c.n_layer, H = c.num_mels / 2;
   if (!m->tc) m->tc = new TcPlan();
   TcPlan* p = m->tc;
+  tc::g_map_fp16 = c.precision == FWN_MIXED_FP16;
   p->w = w;
   p->act.assign((size_t)c.n_block * 8, CUtensorMap());
   p->st32.assign((size_t)c.n_block * 5, CUtensorMap());
@@ -808,6 +830,7 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   a.e = g.e;
   const bool ws = p->wws[f * GEMM_IDS + gemm_id] != 0;
   a.multicast = (kind == EPI_GATE && gate_multicast()) ? 1 : 0;
+  a.fp16 = m->cfg.precision == FWN_MIXED_FP16 ? 1 : 0;
   return tc::tc_launch(a, kind, bn, ws, st);
 }
 
@@ -818,6 +841,7 @@ int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, i
   FWN_CHECK(ksize >= 1 && ksize <= 4 && Cin % 8 == 0 && Cout % 8 == 0, "conv1d_bf16: need ksize<=4 and channel counts that are multiples of 8");
   tc::TcArgs a;
   memset(&a, 0, sizeof(a));
+  tc::g_map_fp16 = false;
   const int Cin16 = (Cin + 15) / 16 * 16, Kpad = (ksize * Cin16 + 63) / 64 * 64, Npad = (Cout + 15) / 16 * 16;
   const int bn = tc::block_n_for(EPI_PLAIN, Cout, false);
   const int pad = causal ? dilation * (ksize - 1) : dilation * (ksize - 1) / 2;

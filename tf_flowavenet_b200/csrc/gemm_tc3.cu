@@ -95,10 +95,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();   // programmatic dependent launch: see tc_ptx.cuh
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      pdl_wait();
       const int nplanes = a.nterms > 3 ? 3 : 2;   // the third weight plane only feeds the 2^-16 terms
       int st = 0;
       uint32_t ph = 0;
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc3_gemm_kernel(const __grid_const
     const int rsub = lane >> 2, c4 = lane & 3;                           // read side: row 8k + rsub, column chunk c4
     double ls_sum = 0.0;
     int it = 0;
+    pdl_wait();
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
       const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
@@ -297,7 +300,17 @@ static int launch_bn(const Tc3Args& a, cudaStream_t st) {
     configured = true;
   }
   const int total = a.g.B * a.tiles_per_utt * a.n_tiles;
-  tc3_gemm_kernel<EPI, BN><<<std::min(total, num_sms()), THREADS, Cfg3<BN>::SMEM, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min(total, num_sms()));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Cfg3<BN>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  FWN_CUDA(cudaLaunchKernelEx(&cfg, tc3_gemm_kernel<EPI, BN>, a));
   FWN_LAUNCH_CHECK();
   return 0;
 }

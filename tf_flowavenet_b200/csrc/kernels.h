@@ -20,7 +20,7 @@ int sumsq(const float* z, double* acc, int64_t n, cudaStream_t st);
 int log_p(const float* z, float* out, int64_t n, double* scratch, cudaStream_t st);
 int upsample_weight_norm(const float* v, const float* g, float* w, int s, cudaStream_t st);
 int upsample_stage(const float* in, const float* w, const float* bias, void* out0, void* out1, int B, int Tm, int mels, int s, bool split,
-                   bool bf16, cudaStream_t st);
+                   int out_kind /* 0 fp32, 1 bf16, 2 fp16 */, cudaStream_t st);
 
 // ---- implicit-GEMM description shared by the CUDA-core (fp32) and tcgen05 (bf16) engines.
 //   acc[m, n] = sum_seg sum_{k < seg.K} A_seg[row(m) shifted by seg.shift in time, k] * W[seg.koff + k, n]
@@ -91,6 +91,6 @@ struct FrontArgs {
 int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st);
 // mixed mode: gather + ActNorm + bf16 cast of the pass-through half: A0[row, q] = a(row, q), q < nq, row pitch kq (zero padded)
 int front_pack(const float* X, int Cx, int nq, int kq, const int* off2log, const float* an_b, const float* an_s, void* A0, int64_t rows,
-               cudaStream_t st);
+               bool fp16, cudaStream_t st);
 
 }  // namespace fwn

@@ -53,6 +53,12 @@ static float bf2f(uint16_t h) {
   memcpy(&f, &u, 4);
   return f;
 }
+static uint16_t f2h(float f) {   // IEEE half, round-to-nearest-even (host side of __float2half_rn)
+  const __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
 static uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -96,8 +102,8 @@ int model_create(const fwn_config* cfg, Model** out) {
   FWN_CHECK(cfg->num_mels >= 2 && cfg->num_mels % 2 == 0, "num_mels=%d must be even (c is split in halves, model.py:125)", cfg->num_mels);
   FWN_CHECK(cfg->filter_size >= 16 && cfg->filter_size % 16 == 0, "filter_size=%d must be a multiple of 16", cfg->filter_size);
   FWN_CHECK(cfg->n_upsample >= 1 && cfg->n_upsample <= 4, "n_upsample out of range");
-  FWN_CHECK(cfg->precision == FWN_FP32 || cfg->precision == FWN_MIXED_BF16, "unknown precision %d", cfg->precision);
-  if (cfg->precision == FWN_MIXED_BF16)
+  FWN_CHECK(cfg->precision == FWN_FP32 || is_mixed(cfg->precision), "unknown precision %d", cfg->precision);
+  if (is_mixed(cfg->precision))
     FWN_CHECK(cfg->num_mels % 8 == 0 && cfg->filter_size == 256, "mixed precision needs num_mels %% 8 == 0 and filter_size 256 (TMA strides / tile shape)");
   Model* m = new Model();
   m->cfg = *cfg;
@@ -269,7 +275,8 @@ struct WBump {
 constexpr size_t IN_WALL = size_t(1) << 62;  // tag on offsets that point into the fp32 region
 
 // Store a [K][N] matrix either as fp32 [K][N] in the fp32 region (fp32 engines) or bf16 [Npad][Kpad] (tcgen05 engine, K-major B operand).
-static size_t store_matrix(WBump& bw, Bump& b, const PMat& w, int K, int N, bool bf16, int* ld_out) {
+// `bf16`: 0 = fp32 operand, 1 = bf16, 2 = fp16 (the precision enum)
+static size_t store_matrix(WBump& bw, Bump& b, const PMat& w, int K, int N, int bf16, int* ld_out) {
   if (!bf16) {
     size_t off = bw.alloc((size_t)K * N);
     for (size_t i = 0; i < (size_t)K * N; ++i) { bw.v[off + i] = (float)w.v[i]; bw.code[off + i] = w.code[i]; }
@@ -280,7 +287,7 @@ static size_t store_matrix(WBump& bw, Bump& b, const PMat& w, int K, int N, bool
   size_t off = b.alloc((size_t)Kpad * Npad * 2);
   uint16_t* d = reinterpret_cast<uint16_t*>(b.buf.data() + off);
   for (int n = 0; n < N; ++n)
-    for (int k = 0; k < K; ++k) d[(size_t)n * Kpad + k] = f2bf((float)w.v[(size_t)k * N + n]);
+    for (int k = 0; k < K; ++k) d[(size_t)n * Kpad + k] = bf16 == 2 ? f2h((float)w.v[(size_t)k * N + n]) : f2bf((float)w.v[(size_t)k * N + n]);
   *ld_out = Kpad;
   return off;
 }
@@ -335,7 +342,7 @@ struct CMap { int m, o; };
 int model_prepack(Model* m, cudaStream_t st) {
   const fwn_config& c = m->cfg;
   const int F = c.filter_size, L = c.n_layer, H = c.num_mels / 2;
-  const bool bf16 = c.precision == FWN_MIXED_BF16;
+  const int bf16 = is_mixed(c.precision) ? c.precision : 0;   // 0 fp32 operands, 1 bf16, 2 fp16
   HostParams hp;
   hp.m = m;
   hp.raw.resize((size_t)m->raw_floats);
@@ -463,7 +470,7 @@ int model_prepack(Model* m, cudaStream_t st) {
             for (int q = 0; q < nq; ++q)
               for (int ch = 0; ch < F; ++ch) wt[((size_t)k * k16 + q) * F + ch] = w[((size_t)k * nq + q) * F + ch];
           int ld;
-          fo.front_wtc = store_matrix(bw, b, wt, 3 * k16, F, true, &ld);
+          fo.front_wtc = store_matrix(bw, b, wt, 3 * k16, F, bf16, &ld);
           fp.front_ld = ld;
           fp.front_k16 = k16;
         }
@@ -617,7 +624,10 @@ int model_prepack(Model* m, cudaStream_t st) {
   model_drop_graphs(m);
   m->packed = true;
   m->plan_B = m->plan_T = -1;  // tensor maps (tcgen05 engine) must be rebuilt
-  return train_after_prepack(m);     // training enabled: rebuild the state that points into the pack buffer
+  // training enabled: rebuild the state that points into the new pack buffer, then produce the operands that exist only on the
+  // device (the transposed dgrad planes) -- a re-prepack after fwn_train_enable must leave the handle ready for fwn_loss_and_grads
+  if (train_after_prepack(m)) return 1;
+  return m->keep_map ? train_repack(m, st) : 0;
 }
 
 // ---------------------------------------------------------------- optional CUDA-event profiling
@@ -663,7 +673,7 @@ int model_plan(const Model* m, int B, int T, Workspace* w, char* base) {
   FWN_CHECK(B > 0 && T > 0, "empty input: B=%d T=%d", B, T);
   FWN_CHECK(T % m->hop == 0, "T=%d is not a multiple of the hop size %d (upsample_scales product; tfrecord.py:53)", T, m->hop);
   FWN_CHECK(T % (1 << c.n_block) == 0, "T=%d is not a multiple of 2^n_block=%d (squeeze, model.py:226)", T, 1 << c.n_block);
-  const size_t as = c.precision == FWN_MIXED_BF16 ? 2 : 4;
+  const size_t as = is_mixed(c.precision) ? 2 : 4;
   const int F = c.filter_size, H = c.num_mels / 2;
   const size_t M0 = (size_t)B * T / 2;
   size_t off = 0;
@@ -769,7 +779,7 @@ __global__ void finish_forward_kernel(const double* sums, const double* an_logde
 
 int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st) {
   const fwn_config& c = m->cfg;
-  const bool bf16 = c.precision == FWN_MIXED_BF16;
+  const bool bf16 = is_mixed(c.precision);
   int Tm = T / m->hop;
   const float* in = c_in;
   for (int i = 0; i < c.n_upsample; ++i) {
@@ -780,10 +790,10 @@ int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, i
     prof_begin(const_cast<Model*>(m), PROF_UPSAMPLE, bytes, st);
     const_cast<Model*>(m)->launches++;
     if (last) {
-      if (upsample_stage(in, m->up_w[i], m->up_b[i], w.cA, w.cB, B, Tm, c.num_mels, s, true, bf16, st)) return 1;
+      if (upsample_stage(in, m->up_w[i], m->up_b[i], w.cA, w.cB, B, Tm, c.num_mels, s, true, bf16 ? c.precision : 0, st)) return 1;
     } else {
       float* out = w.up[i & 1];
-      if (upsample_stage(in, m->up_w[i], m->up_b[i], out, nullptr, B, Tm, c.num_mels, s, false, false, st)) return 1;
+      if (upsample_stage(in, m->up_w[i], m->up_b[i], out, nullptr, B, Tm, c.num_mels, s, false, 0, st)) return 1;
       in = out;
     }
     prof_end(const_cast<Model*>(m), st);
@@ -811,7 +821,7 @@ int finish_forward(const double* sums, const double* an_logdet, float* logp_out,
 static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, int B, int Ti, bool reverse, cudaStream_t st) {
   const fwn_config& c = m->cfg;
   const int F = c.filter_size, L = c.n_layer;
-  const bool bf16 = c.precision == FWN_MIXED_BF16;
+  const bool bf16 = is_mixed(c.precision);
   auto shift_of = [&](int k, int d) { return c.causal ? (k - 2) * d : (k - 1) * d; };  // modules.py:12-15,27
 
   FrontArgs fa;
@@ -841,7 +851,7 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     // mixed mode: tiny gather/cast kernel, then the front conv is three time-shifted K segments on the tcgen05 engine
     const int kq = (fp.nq + 7) / 8 * 8;
     m->launches++;
-    if (front_pack(X, fp.Cx, fp.nq, kq, fp.off2log, fa.an_b, fa.an_s, w.a0, (int64_t)B * Ti, st)) return 1;
+    if (front_pack(X, fp.Cx, fp.nq, kq, fp.off2log, fa.an_b, fa.an_s, w.a0, (int64_t)B * Ti, c.precision == FWN_MIXED_FP16, st)) return 1;
     GemmArgs g = {};
     g.B = B; g.Ti = Ti;
     for (int k = 0; k < 3; ++k) g.seg[k] = Seg{w.a0, kq, fa.shift[k], fp.nq, k * fp.front_k16};

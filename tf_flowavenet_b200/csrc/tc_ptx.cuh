@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace fwn {
@@ -106,6 +107,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Programmatic dependent launch.  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch,
+// bias / resident-weight staging -- none of which touches data the predecessor produces) overlaps the predecessor's tail;
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -238,6 +245,8 @@ template <int BN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// same with fp16 operands (a_format = b_format = 0); the accumulator stays fp32
+constexpr uint32_t IDESC_BF16_BITS = (1u << 7) | (1u << 10);
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -254,6 +263,33 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   lo = __low2float(v);
   hi = __high2float(v);
+}
+// 16-bit activation storage of the mixed modes: bf16, or fp16 when `fp16` (a launch-uniform flag) is set
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool fp16) {
+  if (fp16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ void unpack16(uint32_t u, float& lo, float& hi, bool fp16) {
+  if (fp16) {
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+    lo = f.x;
+    hi = f.y;
+  } else {
+    unpack_bf16(u, lo, hi);
+  }
+}
+// tanh(f) * sigmoid(g) to fp32 accuracy from 2 ex2 + 1 rcp (the fp16 mode's gate: tanh.approx's 2^-11 absolute error would
+// otherwise dominate the 2^-12 relative rounding of fp16 storage):  (E - 1) / ((E + 1)(1 + G)),  E = e^{2f}, G = e^{-g}
+__device__ __forceinline__ float gate_accurate(float f, float g) {
+  f = fminf(fmaxf(f, -15.f), 15.f);       // tanh saturates to +-1 in fp32 beyond |f| ~ 9; keeps E finite
+  g = fmaxf(g, -60.f);                    // G <= e^60: (E+1)(1+G) stays finite
+  float E, G;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E) : "f"(f * 2.8853900817779268f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(g * -1.4426950408889634f));
+  return __fdividef(E - 1.f, (E + 1.f) * (1.f + G));
 }
 
 

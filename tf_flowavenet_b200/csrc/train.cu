@@ -211,8 +211,9 @@ int train_enable(Model* m, cudaStream_t st) {
   FWN_CHECK(m, "null handle");
   FWN_CHECK(m->cfg.precision == FWN_FP32, "training runs on the fp32 engines: create the model with precision FWN_FP32");
   m->keep_map = true;
-  if (model_prepack(m, st)) return 1;   // builds the gather map and, through train_after_prepack, the training state
-  return train_repack(m, st);           // the transposed planes do not exist on the host: produce them (and re-derive the rest) on the device
+  // builds the gather map and the training state, then re-derives every operand on the device (train_repack): the transposed dgrad
+  // planes do not exist on the host
+  return model_prepack(m, st);
 }
 int train_after_prepack(Model* m) { return m->keep_map ? train_build(m) : 0; }
 

@@ -1,7 +1,7 @@
 """Hyper-parameters of the path: the fields FloWaveNet.__init__ reads (reference hparams.py:6-50, model.py:288-314)
 as a plain object, plus the two shipped presets.  ``dtype`` selects the numeric mode:
-'float32' = fp32 parity mode; 'bfloat16' (aliases 'float16', 'mixed') = bf16 operands with fp32 accumulate.
-The reference's own mixed mode is fp16 + loss-scale 64 (hparams.py:9-10); bf16 is a documented deviation."""
+'float32' = fp32 parity mode; 'float16' = fp16 operands with fp32 accumulate, the reference's own mixed dtype (hparams.py:9-10:
+fp16 compute, fp32 master weights, loss scale 64 for training); 'bfloat16' (alias 'mixed') = bf16 operands with fp32 accumulate."""
 
 
 class HParams:

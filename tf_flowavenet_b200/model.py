@@ -188,8 +188,10 @@ class Block:
         return self.forward(x, c, g)
 
 
+# hparams.dtype -> numeric mode.  'float16' is the reference's own mixed dtype (hparams.py:9: fp16 compute, fp32 master weights);
+# 'bfloat16' / 'mixed' keep bf16 operands (the round-1 throughput mode; same speed, 8x coarser operand rounding).
 _PRECISION = {"float32": _lib.FWN_FP32, "fp32": _lib.FWN_FP32, "bfloat16": _lib.FWN_MIXED_BF16, "bf16": _lib.FWN_MIXED_BF16,
-              "float16": _lib.FWN_MIXED_BF16, "mixed": _lib.FWN_MIXED_BF16}
+              "float16": _lib.FWN_MIXED_FP16, "fp16": _lib.FWN_MIXED_FP16, "half": _lib.FWN_MIXED_FP16, "mixed": _lib.FWN_MIXED_BF16}
 
 
 class FloWaveNet:
