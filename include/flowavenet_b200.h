@@ -118,6 +118,15 @@ int fwn_params_ptr(fwn_handle h, float** dev_ptr); /* the flat variable vector i
 int fwn_loss_and_grads(fwn_handle h, const float* x, const float* c, const int32_t* g, int B, int T, float* logp_out,
                        float* logdet_out, float* grads, int64_t grad_floats, void* workspace, int64_t workspace_bytes,
                        void* stream);
+/* Gradient buckets for overlapping the tower average (utils.average_gradients, utils.py:34-60; train.py:75-77) with the backward
+ * pass.  The flat gradient is produced back to front: bucket 0 = the variables of the LAST block (39 % of all parameters for
+ * hparams.py), ..., bucket n_block-1 = block 0, then the upsampler variables (and the speaker embeddings when present).  Each
+ * bucket is one contiguous range [offset, offset+count) of the flat gradient; the ranges tile [0, fwn_param_floats).
+ * fwn_grad_bucket_wait makes `consumer_stream` wait (cudaStreamWaitEvent) until bucket k of the LAST fwn_loss_and_grads call is
+ * final, so an all-reduce enqueued there runs while the backward pass of the earlier blocks is still executing. */
+int fwn_grad_bucket_count(fwn_handle h);
+int fwn_grad_bucket_range(fwn_handle h, int bucket, int64_t* offset, int64_t* count);
+int fwn_grad_bucket_wait(fwn_handle h, int bucket, void* consumer_stream);
 /* tf.global_norm of the gradient vector (train.py:29) -> device scalar */
 int fwn_grad_global_norm(fwn_handle h, const float* grads, float* norm_out, void* stream);
 /* clip_by_global_norm(clip_norm) + tf.train.AdamOptimizer.apply_gradients (train.py:27-31,76-81) + device-side re-pack of every
@@ -130,6 +139,11 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
  * 3 terms (a1w1 + a1w2 + a2w1) keep ~2^-16..2^-18 per product at half the tensor work (default for the training step; gradients
  * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
+/* fp32 training, parity setting: on != 0 runs the FORWARD GEMMs of fwn_loss_and_grads on the CUDA-core engine (round-to-nearest
+ * FFMA chains) and only the backward GEMMs on the split tensor-core engine.  The tensor cores' fp32 accumulator truncates; the
+ * resulting bias (5e-6 on the forward activations) is amplified by the backward pass on gradients that are small differences of
+ * large sums.  With it every variable's gradient stays within 2e-4 of its own max-abs against the float64 oracle on long sequences. */
+int fwn_set_train_exact_forward(fwn_handle h, int on);
 /* Checkpoint / resume of a training run (train.py:190,199-210: tf.train.Saver over the variables and the Adam slots).
  * which: 0 = the flat variable vector, 1 = Adam first moments, 2 = Adam second moments; numel = fwn_param_floats(h).
  * Setting the variables re-derives every packed operand on the device.  The step counter lives with the caller. */

@@ -28,7 +28,7 @@ TF-1.12 run is UNPINNED.  What pins this oracle instead:
      (tests/test_oracle_properties.py): reverse(forward) == id, logdet == slogdet(J)/T,
      zero-init coupling == identity, DDI statistics, squeeze index law, g has no effect.
   3. An independent einsum restatement of the dilated conv and a gradient-of-SAME-conv
-     definition of the transposed conv (tests/test_oracle_primitives.py).
+     definition of the transposed conv (tests/test_oracle_properties.py).
 
 Layout: channels-last [B, T, C] everywhere, exactly like the reference.
 Parameters: a dict name -> torch tensor using the reference's variable names relative to the

@@ -10,7 +10,8 @@ import torch.multiprocessing as mp
 
 from oracle import flowavenet_oracle as O
 from oracle import flowavenet_train_oracle as TO
-from tf_flowavenet_b200.train import average_flat_gradients, broadcast_flat_variables, learning_rate
+from tf_flowavenet_b200.train import (average_flat_gradients, average_flat_gradients_bucketed, broadcast_flat_variables, bucket_ranges,
+                                      learning_rate)
 
 
 def _free_port():
@@ -36,6 +37,24 @@ def _worker(rank, world, port, q):
         ref = TO.average_gradients([TO.loss_and_grads(params, hp, *b)[3] for b in batches])
         ref_flat = torch.cat([ref[k].reshape(-1) for k in names])
         err = float((flat - ref_flat).abs().max())
+        # the bucketed average (what the GPU trainer enqueues per block while the backward pass is still running) is the same
+        # reduction cut at the bucket borders: buckets tile the flat vector exactly and each is averaged on its own
+        shapes = O.param_shapes(hp)
+        buckets = bucket_ranges(shapes, hp.n_block)
+        total = sum((int(torch.tensor(s).prod()) + 3) & ~3 for s in shapes.values())
+        cover = sorted(buckets)
+        tiled = cover[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(cover, cover[1:])) and cover[-1][0] + cover[-1][1] == total
+        padded = torch.zeros(total, dtype=torch.float64)
+        off = 0
+        for k, s in shapes.items():      # the library's flat layout: variables in schema order, each padded to 4 floats
+            n = mine[k].numel()
+            padded[off:off + n] = mine[k].reshape(-1)
+            off += (n + 3) & ~3
+        one_shot = padded.clone()
+        average_flat_gradients(one_shot)
+        average_flat_gradients_bucketed(padded, buckets)
+        err = max(err, float((padded - one_shot).abs().max()), 0.0 if tiled else 1.0)
+        err = max(err, 0.0 if buckets[0][0] == max(b[0] for b in buckets[:hp.n_block]) else 1.0)   # last block is produced first
         # clip + Adam on the averaged gradient: all ranks must agree bit for bit
         clipped, norm = TO.clip_by_global_norm({"g": flat}, 1.0)
         m, v = {"g": torch.zeros_like(flat)}, {"g": torch.zeros_like(flat)}

@@ -45,9 +45,13 @@ SIGNATURES = {
     "fwn_grad_floats": (_l, [_p]),
     "fwn_params_ptr": (_i, [_p, C.POINTER(_p)]),
     "fwn_loss_and_grads": (_i, [_p, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _l, _p, _l, _p]),
+    "fwn_grad_bucket_count": (_i, [_p]),
+    "fwn_grad_bucket_range": (_i, [_p, _i, C.POINTER(_l), C.POINTER(_l)]),
+    "fwn_grad_bucket_wait": (_i, [_p, _i, _p]),
     "fwn_grad_global_norm": (_i, [_p, _fp, _fp, _p]),
     "fwn_apply_gradients": (_i, [_p, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _l, _p]),
     "fwn_set_split_terms": (_i, [_p, _i, _i]),
+    "fwn_set_train_exact_forward": (_i, [_p, _i]),
     "fwn_get_train_state": (_i, [_p, _i, _fp, _l, _p]),
     "fwn_set_train_state": (_i, [_p, _i, _fp, _l, _p]),
     "fwn_repack": (_i, [_p, _p]),

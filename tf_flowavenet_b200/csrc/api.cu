@@ -175,6 +175,23 @@ int fwn_loss_and_grads(fwn_handle h, const float* x, const float* c, const int32
   FWN_CHECK(h, "null handle");
   return train_loss_and_grads(h->m, x, c, g, B, T, logp_out, logdet_out, grads, grad_floats, workspace, workspace_bytes, S(stream));
 }
+int fwn_grad_bucket_count(fwn_handle h) {
+  if (!h) {
+    set_error("null handle");
+    return -1;
+  }
+  const int n = train_bucket_count(h->m);
+  if (n < 0) set_error("training not enabled");
+  return n;
+}
+int fwn_grad_bucket_range(fwn_handle h, int bucket, int64_t* offset, int64_t* count) {
+  FWN_CHECK(h && offset && count, "null argument");
+  return train_bucket_range(h->m, bucket, offset, count);
+}
+int fwn_grad_bucket_wait(fwn_handle h, int bucket, void* consumer_stream) {
+  FWN_CHECK(h, "null handle");
+  return train_bucket_wait(h->m, bucket, S(consumer_stream));
+}
 int fwn_grad_global_norm(fwn_handle h, const float* grads, float* norm_out, void* stream) {
   FWN_CHECK(h && grads && norm_out, "null argument");
   return train_grad_norm(h->m, grads, norm_out, S(stream));
@@ -190,6 +207,11 @@ int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms) {
   h->m->terms_infer = h->m->cur_terms = inference_terms;
   h->m->terms_train = training_terms;
   model_drop_graphs(h->m);   // captured launches carry the old setting
+  return 0;
+}
+int fwn_set_train_exact_forward(fwn_handle h, int on) {
+  FWN_CHECK(h, "null handle");
+  h->m->train_exact_fwd = on != 0;
   return 0;
 }
 int fwn_get_train_state(fwn_handle h, int which, float* dev_dst, int64_t numel, void* stream) {

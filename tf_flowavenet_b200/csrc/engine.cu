@@ -40,7 +40,7 @@ int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowP
     const char* simt_env = getenv("FWN_SIMT_FAMILIES");   // read per call: a debugging script flips it between passes
     const int simt_mask = simt_env ? atoi(simt_env) : 0;
     const int fam = gemm_id == GEMM_FRONT ? 1 : gemm_id == GEMM_FINAL ? 8 : gemm_id == GEMM_ZERO ? 16 : gemm_id >= GEMM_RS0 ? 4 : 2;
-    if (w3.p && fp32_split_engine() && !(simt_mask & fam) && tc3_supported(g)) return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, m->cur_terms, st);
+    if (w3.p && fp32_split_engine() && !m->force_simt && !(simt_mask & fam) && tc3_supported(g)) return tc3_gemm(g, kind, w3.p, w3.Kpad, w3.Npad, m->cur_terms, st);
     if (gemm_id == GEMM_FRONT) {   // the fp32 [3][nq][F] layout has tap k at row k*nq; Seg.koff carries the plane layout (k*front_k16)
       GemmArgs gg = g;
       for (int s = 0; s < gg.nseg; ++s) gg.seg[s].koff = s * fp.nq;

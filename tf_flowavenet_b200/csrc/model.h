@@ -85,6 +85,9 @@ struct Model {
   TrainState* train = nullptr;
   // bf16 split terms per fp32 product on the tensor cores: 6 = every product down to 2^-24, 3 = ~2^-16 per product (fwn_set_split_terms)
   int terms_infer = 6, terms_train = 3, cur_terms = 6;
+  // fp32 training, parity setting: run the FORWARD GEMMs of the training step on the CUDA-core engine (round-to-nearest FFMA chains).
+  // The tensor cores' accumulator truncates, a bias the backward pass amplifies on cancellation-heavy gradients.
+  bool train_exact_fwd = false, force_simt = false;
   bool packed = false, rev_ok = false;
   char* pack = nullptr;
   size_t pack_bytes = 0;

@@ -46,6 +46,11 @@ struct TrainState {
   size_t ev_next = 0;
   cudaEvent_t set_done[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> cond_ready;   // per block: the conditioning projections of its flows are in the tape
+  // Gradient buckets in PRODUCTION order (block n-1 first, ..., block 0, then the upsampler / speaker-embedding rest): contiguous
+  // ranges of the flat gradient whose values are final once `ready` has fired, so the tower average of bucket k (an all-reduce on
+  // the caller's communication stream, utils.py:34-60) overlaps the backward pass of the blocks still to come.
+  struct Bucket { int64_t off, count; int64_t wall0, wall1; int work0, work1; cudaEvent_t ready; };
+  std::vector<Bucket> buckets;
   cudaEvent_t next_event() {
     if (ev.empty()) {
       ev.resize(64);
@@ -66,6 +71,7 @@ void train_free(Model* m) {
   for (auto e : t->ev) cudaEventDestroy(e);
   for (auto e : t->set_done) if (e) cudaEventDestroy(e);
   for (auto e : t->cond_ready) cudaEventDestroy(e);
+  for (auto& b : t->buckets) if (b.ready) cudaEventDestroy(b.ready);
   if (t->side) cudaStreamDestroy(t->side);
   delete t;
   m->train = nullptr;
@@ -101,16 +107,41 @@ static int train_build(Model* m) {
   m->host_wmap.shrink_to_fit();
   FWN_CUDA(cudaMalloc(&t->gwall, (size_t)m->wall_floats * 4));
   if (upload(&t->d_folds, m->folds)) return 1;
+  // first variable (flat offset) of every block; blocks are contiguous in the flat layout: [upsampler | Block_0 | ... | Block_n-1 | rest]
+  std::vector<int64_t> blk_off(c.n_block + 1);
+  for (int i = 0; i < c.n_block; ++i) blk_off[i] = m->params[m->index.at("Block_" + std::to_string(i) + "/Flow_0/ActNorm/b")].offset;
+  blk_off[c.n_block] = c.gin_channels > 0 ? m->params[m->index.at("speaker_embeddings")].offset : m->raw_floats;
+  auto block_of = [&](int64_t off) { return (int)(std::upper_bound(blk_off.begin(), blk_off.end(), off) - blk_off.begin()) - 1; };
   std::vector<FoldWork> fw;
-  for (size_t i = 0; i < m->folds.size(); ++i) {
-    // wide (16-byte) tiles for the many K <= 768 operands; the few long ones (conditioning convs of the deep blocks, K up to 5120)
-    // keep 32-column tiles so that their CTAs do not become the tail of the launch
-    const int vec = ((m->folds[i].N & 3) == 0 && m->folds[i].K <= 1024) ? 1 : 0;
-    for (int c0 = 0; c0 < m->folds[i].N; c0 += vec ? 128 : 32) fw.push_back(FoldWork{(int)i, c0, vec});
+  std::vector<int> fw_begin(c.n_block + 1, 0);
+  for (int blk = 0; blk < c.n_block; ++blk) {
+    const size_t first = fw.size();
+    for (size_t i = 0; i < m->folds.size(); ++i) {
+      if (block_of(m->folds[i].a) != blk) continue;
+      // wide (16-byte) tiles for the many K <= 768 operands; the few long ones (conditioning convs of the deep blocks, K up to 5120)
+      // keep 32-column tiles so that their CTAs do not become the tail of the launch
+      const int vec = ((m->folds[i].N & 3) == 0 && m->folds[i].K <= 1024) ? 1 : 0;
+      for (int c0 = 0; c0 < m->folds[i].N; c0 += vec ? 128 : 32) fw.push_back(FoldWork{(int)i, c0, vec});
+    }
+    std::stable_sort(fw.begin() + first, fw.end(), [&](const FoldWork& x, const FoldWork& y) { return m->folds[x.desc].K > m->folds[y.desc].K; });   // longest first
+    fw_begin[blk + 1] = (int)fw.size();
   }
-  std::stable_sort(fw.begin(), fw.end(), [&](const FoldWork& x, const FoldWork& y) { return m->folds[x.desc].K > m->folds[y.desc].K; });   // longest first
   t->n_fwork = (int)fw.size();
   if (upload(&t->d_fwork, fw)) return 1;
+  {
+    // wall (packed fp32 operand) range of every block: flows are packed in order, each starting with its front-conv kernel
+    std::vector<int64_t> wall_begin(c.n_block + 1, m->wall_floats);
+    for (int i = 0; i < c.n_block; ++i)
+      wall_begin[i] = reinterpret_cast<const float*>(m->flows[(size_t)i * c.n_flow].front_w) - reinterpret_cast<const float*>(m->pack);
+    for (int i = c.n_block - 1; i >= 0; --i) {
+      TrainState::Bucket b{blk_off[i], blk_off[i + 1] - blk_off[i], wall_begin[i], wall_begin[i + 1], fw_begin[i], fw_begin[i + 1], nullptr};
+      t->buckets.push_back(b);
+    }
+    t->buckets.push_back(TrainState::Bucket{0, blk_off[0], 0, 0, 0, 0, nullptr});                                     // upsampler variables
+    if (blk_off[c.n_block] < m->raw_floats)
+      t->buckets.push_back(TrainState::Bucket{blk_off[c.n_block], m->raw_floats - blk_off[c.n_block], 0, 0, 0, 0, nullptr});   // speaker embeddings
+    for (auto& b : t->buckets) FWN_CUDA(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
+  }
 
   // ---- plane descriptors: forward planes (refreshed after every optimizer step) + transposed planes for dgrad
   std::vector<PlaneDesc> pd;
@@ -324,9 +355,10 @@ static inline int shift_of(const fwn_config& c, int k, int d) { return c.causal 
 // depend on the flow state, so they are computed ahead of the dependent chain -- on the side stream, over a flat row axis (full
 // 128-row tiles instead of one mostly empty tile per utterance) -- straight into the pre-activation tape; the gate GEMM then
 // reduces over the 768 conv inputs only and adds the projection in its epilogue.
+static bool g_exact_fwd = false;   // set for the duration of a forward pass that runs on the CUDA-core engine
 static bool cond_ahead(int Ti, const FlowPack& fp) {
   const char* e = getenv("FWN_COND_AHEAD");   // 0 disables (diagnostics)
-  if (e && e[0] == '0') return false;
+  if ((e && e[0] == '0') || g_exact_fwd) return false;
   return Ti <= 256 && (fp.Kc & 3) == 0 && fp.w3[GEMM_GATE0].p != nullptr;
 }
 static int cond_forward(Model* m, const TrainWs& w, const FlowPack& fp, const Tape& tp, int B, int Ti, cudaStream_t st) {
@@ -560,8 +592,9 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   const fwn_config& c = m->cfg;
   TrainState* t = m->train;
   m->launches = 0;
-  struct TermsGuard { Model* m; ~TermsGuard() { m->cur_terms = m->terms_infer; } } terms_guard{m};
+  struct TermsGuard { Model* m; ~TermsGuard() { m->cur_terms = m->terms_infer; m->force_simt = false; g_exact_fwd = false; } } terms_guard{m};
   m->cur_terms = m->terms_train;
+  m->force_simt = g_exact_fwd = m->train_exact_fwd;   // forward phase only; reset before the backward pass
   const size_t BT = (size_t)B * T;
   const int H = c.num_mels / 2;
   FWN_CUDA(cudaMemcpyAsync(w.X, x, BT * 4, cudaMemcpyDeviceToDevice, st));
@@ -600,6 +633,7 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   }
   if (sumsq(w.X, w.sums + 1, (int64_t)BT, st)) return 1;
   if (finish_forward(w.sums, m->d_an_logdet, logp_out, logdet_out, (double)BT, st)) return 1;
+  m->force_simt = false;
   // ---- backward
   if (dual_stream()) {
     for (auto& e : t->set_done) FWN_CUDA(cudaEventRecord(e, st));   // nothing pending on either scratch set; also orders the memsets above
@@ -609,12 +643,26 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   }
   m->launches++;
   if (logp_bwd(w.X, w.dX, (int64_t)BT, st)) return 1;
-  for (int i = c.n_block - 1; i >= 0; --i)
+  for (int i = c.n_block - 1; i >= 0; --i) {
     for (int j = c.n_flow - 1; j >= 0; --j) {
       const size_t f = (size_t)i * c.n_flow + j;
       const float* Xpost = f + 1 < m->flows.size() ? w.tape[f + 1].xpre : w.X;
       if (flow_backward(m, w, m->flows[f], t->flows[f], w.tape[f], Xpost, B, T >> (i + 1), grads, (int)(f & 1), st)) return 1;
     }
+    // Block i is done: packed-operand gradients -> folded vector -> raw variables for THIS block, behind its weight gradients on
+    // the side stream (the dgrad chain of the next block does not wait for it); then the block's bucket of the flat gradient is final.
+    TrainState::Bucket& bk = t->buckets[(size_t)(c.n_block - 1 - i)];
+    cudaStream_t s1 = dual_stream() ? t->side : st;
+    if (dual_stream()) {   // the ActNorm gradients of the block were written on the main stream
+      cudaEvent_t e = t->next_event();
+      FWN_CUDA(cudaEventRecord(e, st));
+      FWN_CUDA(cudaStreamWaitEvent(s1, e, 0));
+    }
+    m->launches += 2;
+    if (scatter_grad(t->gwall + bk.wall0, t->wmap + bk.wall0, grads, bk.wall1 - bk.wall0, s1)) return 1;
+    if (fold_backward(m->raw, grads, t->d_folds, t->d_fwork + bk.work0, bk.work1 - bk.work0, m->raw_floats, s1)) return 1;
+    FWN_CUDA(cudaEventRecord(bk.ready, s1));
+  }
   if (dual_stream()) {   // join: the conditioning gradient and all weight gradients are complete
     cudaEvent_t e = t->next_event();
     FWN_CUDA(cudaEventRecord(e, t->side));
@@ -642,10 +690,21 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
         return 1;
     }
   }
-  // ---- packed-operand gradients -> folded vector -> raw variables
-  m->launches += 2;
-  if (scatter_grad(t->gwall, t->wmap, grads, m->wall_floats, st)) return 1;
-  if (fold_backward(m->raw, grads, t->d_folds, t->d_fwork, t->n_fwork, m->raw_floats, st)) return 1;
+  // the upsampler variables (and the speaker embeddings, whose gradient is identically zero: SURVEY F6) close the gradient
+  for (size_t k = (size_t)c.n_block; k < t->buckets.size(); ++k) FWN_CUDA(cudaEventRecord(t->buckets[k].ready, st));
+  return 0;
+}
+
+int train_bucket_count(const Model* m) { return m->train ? (int)m->train->buckets.size() : -1; }
+int train_bucket_range(const Model* m, int k, int64_t* off, int64_t* count) {
+  FWN_CHECK(m->train && k >= 0 && k < (int)m->train->buckets.size(), "bad gradient bucket %d", k);
+  *off = m->train->buckets[(size_t)k].off;
+  *count = m->train->buckets[(size_t)k].count;
+  return 0;
+}
+int train_bucket_wait(const Model* m, int k, cudaStream_t consumer) {
+  FWN_CHECK(m->train && k >= 0 && k < (int)m->train->buckets.size(), "bad gradient bucket %d", k);
+  FWN_CUDA(cudaStreamWaitEvent(consumer, m->train->buckets[(size_t)k].ready, 0));
   return 0;
 }
 

@@ -79,6 +79,9 @@ int64_t train_workspace_bytes(const Model* m, int B, int T);
 int64_t train_grad_floats(const Model* m);
 int train_loss_and_grads(Model* m, const float* x, const float* c, const int32_t* g, int B, int T, float* logp_out, float* logdet_out,
                          float* grads, int64_t grad_floats, void* ws, int64_t ws_bytes, cudaStream_t st);
+int train_bucket_count(const Model* m);
+int train_bucket_range(const Model* m, int k, int64_t* off, int64_t* count);
+int train_bucket_wait(const Model* m, int k, cudaStream_t consumer);
 int train_grad_norm(Model* m, const float* grads, float* norm_out, cudaStream_t st);
 int train_apply(Model* m, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm, int64_t step, cudaStream_t st);
 int train_repack(Model* m, cudaStream_t st);

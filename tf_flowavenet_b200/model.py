@@ -224,6 +224,7 @@ class FloWaveNet:
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self._device):
             _lib.check(_lib.lib().fwn_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self._device = torch.device("cuda", torch.cuda.current_device()) if self._device.index is None else self._device
         self._hop = int(np.prod(hparams.upsample_scales))
         self._dirty = True
         self._ws = None
@@ -256,6 +257,7 @@ class FloWaveNet:
     def load_variables(self, values):
         """values: {name relative to the model scope -> array-like}; e.g. a converted TF checkpoint."""
         shapes = self.variable_shapes()
+        self._refresh_store()   # the handle may own newer values (DDI, optimizer steps): keep them for the names not in `values`
         for k, v in values.items():
             if k not in shapes:
                 raise KeyError("unknown variable '%s'" % k)
@@ -282,15 +284,27 @@ class FloWaveNet:
             vals[k] = a
         self.load_variables(vals)
 
-    def variables(self):
-        """{relative name -> CUDA tensor}, refreshed from the handle (DDI updates ActNorm variables in place)."""
-        L, out = _lib.lib(), {}
-        for k, shp in self.variable_shapes().items():
-            t = self._store.get(join(self._vs, k))
-            if "/ActNorm/" in k and not self._dirty:
+    def _refresh_store(self):
+        """Copy the handle's live variables back into the store.  Once the variables have been uploaded the HANDLE owns them: the
+        data-dependent ActNorm initialisation and every optimizer step (Trainer) update them on the device, so the store is stale
+        until refreshed -- reading or partially overwriting it without this would mix trained and initial values."""
+        if self._dirty or not getattr(self, "_h", None):
+            return
+        L = _lib.lib()
+        with torch.cuda.device(self._device):
+            for k, shp in self.variable_shapes().items():
+                name = join(self._vs, k)
+                t = self._store.get(name) if name in self._store else None
+                if t is None or tuple(t.shape) != tuple(shp) or not t.is_contiguous() or t.device != self._device:
+                    t = torch.empty(shp, dtype=torch.float32, device=self._device)
+                    self._store[name] = t
                 _lib.check(L.fwn_get_param(self._h, k.encode(), _lib.ptr(t), t.numel(), _lib.stream_ptr()))
-            out[k] = t
-        return out
+
+    def variables(self):
+        """{relative name -> CUDA tensor} of the CURRENT values (what tf.train.Saver would write, train.py:190,252): refreshed from
+        the handle, which owns the live variables after DDI / training steps."""
+        self._refresh_store()
+        return {k: self._store.get(join(self._vs, k)) for k in self.variable_shapes()}
 
     def _sync_params(self):
         if not self._dirty:
@@ -431,21 +445,41 @@ class FloWaveNet:
         return _lib.lib().fwn_last_launches(self._h)
 
     # host-buffer entry points (numpy / pinned torch CPU tensors): the end-to-end call of synthesize.py:44-46
-    def reverse_host(self, z, c, out=None):
+    def _check_host(self, a, c, g, what):
+        """Same validation as _check_xc / _check_g, for HOST buffers: float32, contiguous, [B,T,1] / [B,T/hop,mels] / int32 [B]."""
+        a, c = (t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)) for t in (a, c))
+        for t, n in ((a, what), (c, "c")):
+            if t.is_cuda or t.dim() != 3:
+                raise TypeError("%s must be a host (CPU) array of rank 3" % n)
+        if a.shape[2] != 1 or c.shape[2] != self._cin_channels or c.shape[0] != a.shape[0]:
+            raise ValueError("expected %s [B,T,1] and c [B,T/hop,%d]" % (what, self._cin_channels))
+        if c.shape[1] * self._hop != a.shape[1]:
+            raise ValueError("len(%s)=%d must equal len(c)*hop=%d*%d (tfrecord.py:53)" % (what, a.shape[1], c.shape[1], self._hop))
+        if g is None and self._hparams.gin_channels > 0:
+            raise ValueError('g is None')  # model.py:320-321, 353-354
+        if g is not None:
+            g = (g if isinstance(g, torch.Tensor) else torch.from_numpy(np.asarray(g))).to("cpu", torch.int32).contiguous()
+            if g.dim() != 1 or g.shape[0] != a.shape[0]:
+                raise ValueError("g must hold one speaker id per utterance")
+        return a.float().contiguous(), c.float().contiguous(), g
+
+    def reverse_host(self, z, c, out=None, g=None):
         self._sync_params()
-        z, c = (t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)) for t in (z, c))
+        z, c, g = self._check_host(z, c, g, "z")
         B, T = z.shape[0], z.shape[1]
         out = torch.empty(B, T, 1, dtype=torch.float32, pin_memory=True) if out is None else out
+        if tuple(out.shape) != (B, T, 1) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 host tensor of shape [B,T,1]")
         with torch.cuda.device(self._device):
-            _lib.check(_lib.lib().fwn_reverse_host(self._h, _lib.ptr(z), _lib.ptr(c), None, B, T, _lib.ptr(out)))
+            _lib.check(_lib.lib().fwn_reverse_host(self._h, _lib.ptr(z), _lib.ptr(c), _lib.ptr(g), B, T, _lib.ptr(out)))
         return out
 
-    def forward_host(self, x, c, z_out=None):
+    def forward_host(self, x, c, z_out=None, g=None):
         self._sync_params()
-        x, c = (t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)) for t in (x, c))
+        x, c, g = self._check_host(x, c, g, "x")
         B, T = x.shape[0], x.shape[1]
         lp, ld = ctypes.c_float(), ctypes.c_float()
         with torch.cuda.device(self._device):
-            _lib.check(_lib.lib().fwn_forward_host(self._h, _lib.ptr(x), _lib.ptr(c), None, B, T, _lib.ptr(z_out), ctypes.byref(lp),
+            _lib.check(_lib.lib().fwn_forward_host(self._h, _lib.ptr(x), _lib.ptr(c), _lib.ptr(g), B, T, _lib.ptr(z_out), ctypes.byref(lp),
                                                   ctypes.byref(ld)))
         return lp.value, ld.value

@@ -2,8 +2,9 @@
 clip_gradients (27-32) and utils.average_gradients (utils.py:34-60).
 
 The reference replicates the graph on `hparams.num_gpus` towers inside one process and averages the tower gradients on a
-consolidation device.  Here every tower is one process / one GPU (torchrun); the average is one NCCL all-reduce of the flat
-gradient vector.  Everything else -- loss, gradients, global-norm clip, Adam, re-packing of the derived operands -- runs inside
+consolidation device.  Here every tower is one process / one GPU (torchrun); the average is an NCCL all-reduce of the flat
+gradient vector, issued per block-sized bucket in the order the backward pass finishes them (last block first) on a
+communication stream, so it overlaps the rest of the backward pass.  Everything else -- loss, gradients, global-norm clip, Adam, re-packing of the derived operands -- runs inside
 libflowavenet_b200 (fwn_loss_and_grads / fwn_apply_gradients); there is no CPU or autograd fallback.
 """
 import ctypes
@@ -37,6 +38,57 @@ def average_flat_gradients(flat, group=None):
     return flat
 
 
+def bucket_ranges(variable_shapes, n_block):
+    """[(offset, count)] of the gradient buckets in production order -- the Python twin of fwn_grad_bucket_range: block n-1 first,
+    ..., block 0, then the upsampler variables, then the speaker embeddings if present.  `variable_shapes`: ordered
+    {name -> shape} as FloWaveNet.variable_shapes() returns it; every variable occupies ceil4(numel) floats of the flat vector."""
+    off, starts, total = 0, {}, 0
+    for k, shp in variable_shapes.items():
+        n = 1
+        for s in shp:
+            n *= int(s)
+        starts[k] = off
+        off += (n + 3) & ~3
+    total = off
+    blk = [starts["Block_%d/Flow_0/ActNorm/b" % i] for i in range(n_block)]
+    blk.append(starts.get("speaker_embeddings", total))
+    out = [(blk[i], blk[i + 1] - blk[i]) for i in range(n_block - 1, -1, -1)]
+    out.append((0, blk[0]))
+    if blk[n_block] < total:
+        out.append((blk[n_block], total - blk[n_block]))
+    return out
+
+
+def average_flat_gradients_bucketed(flat, buckets, group=None, waiters=None, stream=None):
+    """utils.average_gradients (utils.py:34-60), one all-reduce per bucket in production order.  With `waiters` (one callable per
+    bucket, each makes the current CUDA stream wait until that bucket is final) and a communication `stream`, the reductions are
+    enqueued asynchronously behind those waits and overlap whatever the producer is still computing; returns the pending work
+    handles (call .wait() on each before reading `flat`).  Without them (CPU / gloo) the buckets are reduced in place, blocking."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()):
+        return []
+    ws = dist.get_world_size(group)
+    if ws < 2:
+        return []
+    nccl = dist.get_backend(group) == "nccl"
+    op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM   # gloo has no AVG: sum, then scale
+    pending = []
+    for k, (off, cnt) in enumerate(buckets):
+        if cnt == 0:
+            continue
+        piece = flat[off:off + cnt]
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                if waiters is not None:
+                    waiters[k]()
+                pending.append(dist.all_reduce(piece, op=op, group=group, async_op=True))
+        else:
+            dist.all_reduce(piece, op=op, group=group)
+            if not nccl:
+                piece.mul_(1.0 / ws)
+    return pending
+
+
 def broadcast_flat_variables(flat, src=0, group=None):
     """Towers share ONE set of variables in the reference (tf.variable_scope reuse, train.py:51-53).  With one process per tower
     the data-dependent ActNorm initialisation (train.py:221,229) would leave every rank with its own statistics, so rank `src`'s
@@ -49,26 +101,53 @@ def broadcast_flat_variables(flat, src=0, group=None):
 class Trainer:
     """One tower.  `group`: torch.distributed process group over which tower gradients are averaged (None = single tower)."""
 
-    def __init__(self, model, group=None, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8, scale=1.0, split_terms=6):
+    def __init__(self, model, group=None, clip_norm=1.0, beta1=0.9, beta2=0.999, epsilon=1e-8, split_terms=6, compute_dtype="float32",
+                 exact_forward=None, overlap_allreduce=True):
+        """model: an fp32 FloWaveNet (fp32 master variables, as utils.fp16_dtype_getter keeps them, utils.py:3-31).
+        compute_dtype: 'float32' = fp32-accurate GEMMs (3-way bf16 split on the tensor cores; `split_terms` products per fp32 product:
+        6 = every product down to 2^-24, 3 = ~2^-16 at half the tensor work).
+        exact_forward (fp32 only; default: on for split_terms=6): forward GEMMs of the step on the CUDA-core engine -- the parity
+        setting that keeps EVERY variable's gradient within 2e-4 of its own max-abs (see fwn_set_train_exact_forward).
+        The static loss scale of the reference (hparams.scale = 64, train.py:62,75-77) exists for fp16 gradients; every mode here
+        accumulates and stores gradients in fp32, so it is 1 and not a parameter."""
         if model._precision != _lib.FWN_FP32:
-            raise ValueError("training runs on the fp32 engines: use hparams.dtype='float32'")
+            raise ValueError("training keeps fp32 master variables: build the model with hparams.dtype='float32' and choose the "
+                             "compute dtype with Trainer(compute_dtype=...)")
+        if compute_dtype not in ("float32",):
+            raise ValueError("unsupported compute_dtype %r" % (compute_dtype,))
         self.model, self.group = model, group
         self.clip_norm, self.beta1, self.beta2, self.epsilon = clip_norm, beta1, beta2, epsilon
-        self.scale = float(scale)  # hparams.scale (train.py:62,75): static loss scale; 1 here (fp32 accumulation everywhere)
+        self.compute_dtype = compute_dtype
         self.global_step = 0
         L = _lib.lib()
         model._sync_params()
         with torch.cuda.device(model._device):
             _lib.check(L.fwn_train_enable(model._h, _lib.stream_ptr()))
-        # split_terms: bf16 products per fp32 product in the training GEMMs.  6 = every product down to 2^-24 (every variable's gradient within
-        # 2e-4 of a float64 reference); 3 = ~2^-16..2^-18 per product at half the tensor work (errors up to ~1e-3 of the largest
-        # gradient entry on cancellation-heavy gradients; ~10x tighter than bf16).  Inference passes always use 6.
         _lib.check(L.fwn_set_split_terms(model._h, 6, int(split_terms)))
+        self.exact_forward = bool(split_terms == 6) if exact_forward is None else bool(exact_forward)
+        _lib.check(L.fwn_set_train_exact_forward(model._h, int(self.exact_forward)))
         self._n = L.fwn_grad_floats(model._h)
         self._np = L.fwn_param_floats(model._h)
         self.grads = torch.zeros(self._n, dtype=torch.float32, device=model._device)
         self._ws = None
         self._out = torch.zeros(3, dtype=torch.float32, device=model._device)
+        # gradient buckets (production order) for the overlapped tower average
+        import ctypes as C
+        off, cnt = C.c_int64(), C.c_int64()
+        self.buckets = []
+        for k in range(L.fwn_grad_bucket_count(model._h)):
+            _lib.check(L.fwn_grad_bucket_range(model._h, k, C.byref(off), C.byref(cnt)))
+            self.buckets.append((off.value, cnt.value))
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self._comm = None
+        self._pending = []
+
+    def param_floats(self):
+        return self._np
+
+    def _towers(self):
+        d = torch.distributed
+        return d.get_world_size(self.group) if (d.is_available() and d.is_initialized()) else 1
 
     def _workspace(self, B, T):
         need = _lib.lib().fwn_train_workspace_bytes(self.model._h, B, T)
@@ -84,16 +163,31 @@ class Trainer:
         m = self.model
         g = m._check_g(g)
         x, c = m._check_xc(x, c, "x")
+        m._sync_params()   # variables loaded since the last step (FloWaveNet.load_variables) reach the handle; Adam slots are kept
         B, T = x.shape[0], x.shape[1]
         ws = self._workspace(B, T)
         with torch.cuda.device(m._device):
             _lib.check(_lib.lib().fwn_loss_and_grads(m._h, _lib.ptr(x), _lib.ptr(c), _lib.ptr(g), B, T, _lib.ptr(self._out[0:]),
                                                     _lib.ptr(self._out[1:]), _lib.ptr(self.grads), self._n, _lib.ptr(ws), ws.numel(),
                                                     _lib.stream_ptr()))
+            if self.overlap_allreduce and self._towers() > 1:
+                # the whole pass is enqueued; each bucket's all-reduce goes on the communication stream behind the event that marks
+                # the bucket final, i.e. it runs while the backward pass of the blocks before it is still executing
+                if self._comm is None:
+                    self._comm = torch.cuda.Stream(device=m._device)
+                L, h, comm = _lib.lib(), m._h, self._comm
+                waiters = [(lambda k=k: _lib.check(L.fwn_grad_bucket_wait(h, k, ctypes.c_void_p(comm.cuda_stream)))) for k in range(len(self.buckets))]
+                self._pending = average_flat_gradients_bucketed(self.grads, self.buckets, self.group, waiters, comm)
         return self._out[0], self._out[1]
 
     def average_gradients(self):
-        """utils.py:34-60 across towers = processes."""
+        """utils.py:34-60 across towers = processes.  With overlap_allreduce the reductions were enqueued by loss_and_grads; here the
+        compute stream only waits for them."""
+        if self._pending:
+            for w in self._pending:
+                w.wait()   # the current stream waits for the collective; the host does not block
+            self._pending = []
+            return
         average_flat_gradients(self.grads[:self._np], self.group)
 
     def apply_gradients(self):
@@ -164,7 +258,8 @@ class Trainer:
         return out
 
     def variables(self):
-        """{variable name -> fresh copy of the current value} (the handle owns the live variables during training)."""
+        """{variable name -> fresh copy of the current value} (the handle owns the live variables during training;
+        FloWaveNet.variables() returns the same values through the model's store)."""
         m, L, out = self.model, _lib.lib(), {}
         with torch.cuda.device(m._device):
             for k, shp in m.variable_shapes().items():
