@@ -139,6 +139,15 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
  * 3 terms (a1w1 + a1w2 + a2w1) keep ~2^-16..2^-18 per product at half the tensor work (default for the training step; gradients
  * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
+/* Compute precision of the training step (the model keeps fp32 master variables either way, utils.py:3-31):
+ *   FWN_FP32        fp32-accurate GEMMs (3-way bf16 split on the tensor cores) -- the parity mode (default)
+ *   FWN_MIXED_BF16  bf16 operands and tape, fp32 accumulation / reductions / gradients: BASELINE config 5 ("bf16").  bf16 keeps
+ *                   fp32's exponent range, so the reference's static loss scale (hparams.scale, train.py:62,75-77) is 1. */
+int fwn_set_train_compute(fwn_handle h, int precision);
+/* Per-op entry of the bf16 weight-gradient kernel (unit parity): dw[k, n] += sum_{b,t} a[b, t + shift, k] dy[b, t, n];
+ * dbias[n] += sum_{b,t} dy[b, t, n] (nullable).  a [B,T,K], dy [B,T,N] bf16 (K, N multiples of 8); dw [K,N], dbias [N] fp32, accumulated.
+ * Reference: tf.gradients of a Conv1D kernel / bias (modules.py:24-33; train.py:62-63). */
+int fwn_wgrad_bf16(const void* a, const void* dy, float* dw, float* dbias, int B, int T, int K, int N, int shift, void* stream);
 /* fp32 training, parity setting: on != 0 runs the FORWARD GEMMs of fwn_loss_and_grads on the CUDA-core engine (round-to-nearest
  * FFMA chains) and only the backward GEMMs on the split tensor-core engine.  The tensor cores' fp32 accumulator truncates; the
  * resulting bias (5e-6 on the forward activations) is amplified by the backward pass on gradients that are small differences of

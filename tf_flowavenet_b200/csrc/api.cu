@@ -209,6 +209,24 @@ int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms) {
   model_drop_graphs(h->m);   // captured launches carry the old setting
   return 0;
 }
+int fwn_set_train_compute(fwn_handle h, int precision) {
+  FWN_CHECK(h, "null handle");
+  FWN_CHECK(precision == FWN_FP32 || precision == FWN_MIXED_BF16, "training compute precision must be FWN_FP32 or FWN_MIXED_BF16");
+  if (precision == FWN_MIXED_BF16)
+    FWN_CHECK(h->m->cfg.filter_size == 256 && h->m->cfg.num_mels % 8 == 0,
+              "bf16 training needs filter_size 256 and num_mels %% 8 == 0 (TMA strides / tile shape)");
+  h->m->train_bf16 = precision == FWN_MIXED_BF16;
+  return 0;
+}
+int fwn_wgrad_bf16(const void* a, const void* dy, float* dw, float* dbias, int B, int T, int K, int N, int shift, void* stream) {
+  FWN_CHECK(a && dy && dw, "null argument");
+  Wgrad16Args w = {};
+  w.seg[0] = Seg{a, K, shift, K, 0};
+  w.nseg = 1;
+  w.dY0 = dy; w.ld0 = N; w.n0cols = N; w.N = N;
+  w.dW = dw; w.ldw = N; w.B = B; w.Ti = T;
+  return wgrad_tc(w, dbias, S(stream));
+}
 int fwn_set_train_exact_forward(fwn_handle h, int on) {
   FWN_CHECK(h, "null handle");
   h->m->train_exact_fwd = on != 0;

@@ -19,6 +19,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 #include "model.h"
 #include "tc_ptx.cuh"
@@ -57,8 +59,10 @@ struct alignas(64) TcArgs {
 // (TMA fill + operand read drop from 192 to 128 bytes per cycle per SM).
 template <int EPI, int BN, bool WS, bool PAIR = false>
 struct Cfg {
-  static constexpr bool STAGED = (EPI == EPI_GATE) || (EPI == EPI_RES_SKIP) || (EPI == EPI_PLAIN && BN == 128);
-  static constexpr bool IN_PLACE = (EPI == EPI_RES_SKIP);                 // staging tile is TMA-loaded, updated in place, TMA-stored
+  static constexpr bool STAGED = (EPI == EPI_GATE) || (EPI == EPI_RES_SKIP) || (EPI == EPI_LINEAR) || (EPI == EPI_PLAIN && BN == 128);
+  // staging tile is TMA-loaded, updated in place, TMA-stored.  LINEAR (backward pass of the 16-bit training mode) is RES_SKIP with
+  // every column a "residual" column: y = alpha (acc + in0), or y = in0 > 0 ? alpha acc : 0 when in0 is a ReLU mask
+  static constexpr bool IN_PLACE = (EPI == EPI_RES_SKIP) || (EPI == EPI_LINEAR);
   static constexpr int OUT_COLS = (EPI == EPI_GATE) ? BN / 2 : BN;        // bf16 output columns per tile
   static constexpr int SUBTILES = STAGED ? OUT_COLS / 64 : 0;             // [128 rows x 64 cols] 16 KB boxes
   static constexpr int STG_BYTES = SUBTILES * BM * 128;
@@ -103,7 +107,10 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
   const bool fp16 = a.fp16 != 0;
   const int col = n_tile * BN + c0;  // global column of v[0]
   float acc[16];
-  {  // bias from shared memory (broadcast 128-bit reads): WS kernels stage their own column tile, the others all columns
+  if (EPI == EPI_PLAIN_F32) {   // no bias (and N may exceed the staged bias range)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+  } else {  // bias from shared memory (broadcast 128-bit reads): WS kernels stage their own column tile, the others all columns
     const float* bp = sbias + (WS ? c0 : col);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -127,10 +134,15 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
       for (int j = 0; j < 4; ++j) {
         // tanh(f) * sigmoid(g) = t + t*tanh(g/2) with t = tanh(f)/2 : 2 MUFU + 3 FP32 ops per output
         const float t0 = 0.5f * tanh_fast(acc[4 * j]), t1 = 0.5f * tanh_fast(acc[4 * j + 2]);
-        const float o0 = fmaf(tanh_fast(0.5f * acc[4 * j + 1]), t0, t0);
-        const float o1 = fmaf(tanh_fast(0.5f * acc[4 * j + 3]), t1, t1);
+        const float h0 = tanh_fast(0.5f * acc[4 * j + 1]), h1 = tanh_fast(0.5f * acc[4 * j + 3]);
+        const float o0 = fmaf(h0, t0, t0);
+        const float o1 = fmaf(h1, t1, t1);
         p[j] = pack_bf16(o0, o1);
+        if (e.tape) acc[4 * j] = fmaf(h0, 0.5f, 0.5f), acc[4 * j + 2] = fmaf(h1, 0.5f, 0.5f);   // sigmoid(g), kept for the backward pass
       }
+      if (e.tape && row_ok)   // training forward: 8 sigmoids = 16 bytes of this thread's row
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.tape) + row * e.F + col / 2) =
+            make_uint4(pack_bf16(acc[0], acc[2]), pack_bf16(acc[4], acc[6]), pack_bf16(acc[8], acc[10]), pack_bf16(acc[12], acc[14]));
     }
     sts128(smem_u32(stg) + stg_off(r, c0 / 2), make_uint4(p[0], p[1], p[2], p[3]));
   } else if (EPI == EPI_RES_SKIP) {
@@ -162,6 +174,49 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
     }
     sts128(sbase + stg_off(r, c0), make_uint4(p[0], p[1], p[2], p[3]));
     sts128(sbase + stg_off(r, c0 + 8), make_uint4(p[4], p[5], p[6], p[7]));
+  } else if (EPI == EPI_LINEAR) {
+    const uint32_t sbase = smem_u32(stg);
+    float in[16];
+    if (have_in) {
+      const uint4 h0 = inp[0], h1 = inp[1];
+      const uint32_t hu[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) unpack16(hu[j], in[2 * j], in[2 * j + 1], fp16);
+    }
+    uint32_t p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float lo = acc[2 * j], hi = acc[2 * j + 1];
+      if (have_in && !e.mask_mode) { lo += in[2 * j]; hi += in[2 * j + 1]; }
+      lo *= e.alpha;
+      hi *= e.alpha;
+      if (have_in && e.mask_mode) {
+        lo = in[2 * j] > 0.f ? lo : 0.f;
+        hi = in[2 * j + 1] > 0.f ? hi : 0.f;
+      }
+      p[j] = pack16(lo, hi, fp16);
+    }
+    sts128(sbase + stg_off(r, c0), make_uint4(p[0], p[1], p[2], p[3]));
+    sts128(sbase + stg_off(r, c0 + 8), make_uint4(p[4], p[5], p[6], p[7]));
+  } else if (EPI == EPI_PLAIN_F32) {
+    if (!row_ok) return;
+    float* o = reinterpret_cast<float*>(e.out0) + row * e.ld + col;
+    if (col + 15 < a.N && (e.ld & 3) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float4 y = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        if (e.accum) {
+          const float4 old = o4[k];
+          y.x += old.x; y.y += old.y; y.z += old.z; y.w += old.w;
+        }
+        o4[k] = y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col + j < a.N) o[j] = e.accum ? o[j] + acc[j] : acc[j];
+    }
   } else if (EPI == EPI_PLAIN) {
     uint32_t p[8];
 #pragma unroll
@@ -195,6 +250,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
       const int q = q0 + p;
       if (q >= e.nq) break;
       const float log_s = acc[2 * p], tt = acc[2 * p + 1];
+      if (e.out1) *reinterpret_cast<float2*>(reinterpret_cast<float*>(e.out1) + row * e.ld + 2 * q) = make_float2(log_s, tt);   // tape
       const int oa = __ldg(e.a_off + q), ob = __ldg(e.b_off + q);
       float xa = xr[oa], xb = xr[ob];
       if (!e.reverse) {
@@ -216,7 +272,7 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
 // AFFINE fast path on registers: 16 accumulator columns = 8 adjacent (pass-through, transformed) pairs = 16 consecutive floats
 // of the thread's x row, already loaded into x4[0..3]; ActNorm + coupling applied in place in registers.
 __device__ __forceinline__ void affine16_regs(const EpiArgs& e, const float* sbias, int col, const uint32_t* v, float4* x4, bool row_ok,
-                                              double& ls_sum) {
+                                              double& ls_sum, int64_t row) {
   const float4* bp = reinterpret_cast<const float4*>(e.an_b + col);
   const float4* sp = reinterpret_cast<const float4*>(e.an_s + col);
   const int bo = e.b_odd;
@@ -228,6 +284,8 @@ __device__ __forceinline__ void affine16_regs(const EpiArgs& e, const float* sbi
     const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
     const float ac[4] = {__uint_as_float(v[4 * k]) + bias4.x, __uint_as_float(v[4 * k + 1]) + bias4.y,
                          __uint_as_float(v[4 * k + 2]) + bias4.z, __uint_as_float(v[4 * k + 3]) + bias4.w};
+    if (e.out1 && row_ok)   // training forward: (log_s, t) pairs of this row, in column order (the tape of affine_bwd)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out1) + row * e.ld + col + 4 * k) = make_float4(ac[0], ac[1], ac[2], ac[3]);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const float log_s = ac[2 * h], tt = ac[2 * h + 1];
@@ -313,7 +371,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   }
   for (int i = threadIdx.x; i < C::BIAS_BYTES / 4; i += C::THREADS) {
     const int col = (WS ? ws_n * BN : 0) + i;
-    sbias[i] = col < a.N ? __ldg(a.e.bias + col) : 0.f;
+    sbias[i] = (col < a.N && a.e.bias) ? __ldg(a.e.bias + col) : 0.f;
   }
   if (warp == 1) {
     if (PAIR) tmem_alloc_2sm<C::TMEM_COLS>(tmem_ptr);
@@ -329,7 +387,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
 
   // which input map (if any) feeds the epilogue of column tile n_tile (RES_SKIP only)
   auto input_map_of = [&](int n_tile) -> int {
-    if (EPI != EPI_RES_SKIP) return -1;
+    if (EPI != EPI_RES_SKIP && EPI != EPI_LINEAR) return -1;
     const int which = (a.e.has_res && n_tile * BN < a.e.F) ? 0 : 1;
     return a.has_in[which] ? which : -1;
   };
@@ -485,7 +543,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
         // RES_SKIP: this thread's slice of the staged input tile (already landed: in_full was waited for), fetched with
         // explicit shared-space loads BEFORE the accumulator wait so their latency overlaps it
         uint4 inp[LDW >= 8 ? LDW / 8 : 1];
-        if (EPI == EPI_RES_SKIP && have_in) {
+        if ((EPI == EPI_RES_SKIP || EPI == EPI_LINEAR) && have_in) {
           const uint32_t sbase = smem_u32(stg);
 #pragma unroll
           for (int k = 0; k < LDW / 8; ++k) inp[k] = lds128(sbase + stg_off(r, cc + 8 * k));
@@ -495,7 +553,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
         tmem_ld_wait();
         if (EPI == EPI_AFFINE && xfast) {
 #pragma unroll
-          for (int j = 0; j < LDW; j += 16) affine16_regs(a.e, sbias, gcol + j, v + j, xv + j / 4, row_ok, ls_sum);
+          for (int j = 0; j < LDW; j += 16) affine16_regs(a.e, sbias, gcol + j, v + j, xv + j / 4, row_ok, ls_sum, row);
           if (row_ok) {
 #pragma unroll
             for (int k = 0; k < LDW / 4; ++k) xp[k] = xv[k];
@@ -518,7 +576,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
         __syncwarp();
         if (lane == 0) {
           int om = 0, ocol = n_tile * C::OUT_COLS;
-          if (EPI == EPI_RES_SKIP) {
+          if (EPI == EPI_RES_SKIP || EPI == EPI_LINEAR) {
             om = (a.e.has_res && n_tile * BN < a.e.F) ? 0 : 1;
             ocol = (n_tile * BN) % a.e.F;
           }
@@ -667,8 +725,20 @@ int block_n_for(EpiKind kind, int N, bool model_path) {
 }
 
 int tc_launch(TcArgs& a, EpiKind kind, int bn, bool ws, cudaStream_t st) {
-  FWN_CHECK(a.n_tiles * bn <= 512, "tc_gemm: N=%d too wide", a.N);
+  FWN_CHECK(kind == EPI_PLAIN_F32 || a.n_tiles * bn <= 512, "tc_gemm: N=%d too wide", a.N);
   switch (kind) {
+    case EPI_LINEAR:
+      FWN_CHECK(bn == 128, "linear runs at BN=128");
+      return ws ? launch<EPI_LINEAR, 128, true>(a, st) : launch<EPI_LINEAR, 128, false>(a, st);
+    case EPI_PLAIN_F32:
+      switch (bn) {
+        case 16: return launch<EPI_PLAIN_F32, 16, false>(a, st);
+        case 32: return launch<EPI_PLAIN_F32, 32, false>(a, st);
+        case 64: return launch<EPI_PLAIN_F32, 64, false>(a, st);
+        case 128: return launch<EPI_PLAIN_F32, 128, false>(a, st);
+        default: return launch<EPI_PLAIN_F32, 256, false>(a, st);
+      }
+    case EPI_GATE_BWD: break;
     case EPI_GATE:
       FWN_CHECK(bn == 256, "gate needs BN=256");
       return a.multicast ? launch<EPI_GATE, 256, false, true>(a, st) : launch<EPI_GATE, 256, false, false>(a, st);
@@ -858,6 +928,142 @@ int tc_conv1d(const void* x, const void* w, const float* bias, void* y, int B, i
   a.e.bias = bias; a.e.out0 = y; a.e.ld = Cout; a.e.relu = relu; a.e.F = Cout;
   if (bn == 128 && tc::make_store_map(&a.mapOut[0], y, B, T, Cout, Cout)) return 1;  // staged TMA-store epilogue
   return tc::tc_launch(a, EPI_PLAIN, bn, false, st);
+}
+
+// ---------------------------------------------------------------- generic 16-bit GEMM (training step): cached tensor maps
+namespace {
+struct MapKey {
+  const void* base;
+  int64_t ld;
+  int C, Ti, B, box_c, box_rows, fp16;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && ld == o.ld && C == o.C && Ti == o.Ti && B == o.B && box_c == o.box_c && box_rows == o.box_rows && fp16 == o.fp16;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix((uint64_t)k.ld); mix((uint64_t)k.C); mix((uint64_t)k.Ti); mix((uint64_t)k.B);
+    mix((uint64_t)k.box_c * 4096 + (uint64_t)k.box_rows * 2 + (uint64_t)k.fp16);
+    return (size_t)h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> c;
+  return c;
+}
+}  // namespace
+
+// 16-bit tensor [B, Ti, C] with row pitch ld (elements) -> 3-D map with a (box_c, box_rows, 1) box, 128B swizzle, zero OOB fill.
+// B == 0 encodes a 2-D weight matrix [Ti = rows(N), C = K] with a (box_c, box_rows) box.  Encoded once per distinct key.
+int tc_map_3d(CUtensorMap* out, const void* base, int C, int Ti, int B, int64_t ld, int box_c, int box_rows, bool fp16) {
+  const MapKey key{base, ld, C, Ti, B, box_c, box_rows, fp16 ? 1 : 0};
+  auto& cache = map_cache();
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (cache.size() > 200000) cache.clear();
+  tc::EncodeFn enc = tc::get_encode();
+  FWN_CHECK(enc, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  FWN_CHECK((ld * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) % 16) == 0, "TMA needs 16-byte aligned rows (ld=%lld)", (long long)ld);
+  const CUtensorMapDataType dt = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r;
+  if (B > 0) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Ti, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)Ti};
+    cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)Ti};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  FWN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B=%d Ti=%d C=%d ld=%lld box=%dx%d) failed: %d", B, Ti, C, (long long)ld, box_c, box_rows, (int)r);
+  cache.emplace(key, *out);
+  return 0;
+}
+
+int tc_gemm16(const GemmArgs& g0, EpiKind kind, const void* W, int Kpad, int Npad, bool fp16, cudaStream_t st) {
+  if (g0.B <= 0 || g0.Ti <= 0 || g0.N <= 0) return 0;
+  GemmArgs g = g0;
+  bool shifted = false;
+  for (int s = 0; s < g.nseg; ++s) shifted = shifted || g.seg[s].shift != 0;
+  if (!shifted && (int64_t)g.B * g.Ti < (int64_t(1) << 31)) {   // 1x1 convs: utterance borders do not matter -> one flat row axis, full tiles
+    g.Ti = g.B * g.Ti;
+    g.B = 1;
+  }
+  const int F = g.e.F;
+  int total_chunks = 0;
+  tc::TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nseg = g.nseg;
+  for (int s = 0; s < g.nseg; ++s) {
+    const Seg& sg = g.seg[s];
+    if (tc_map_3d(&a.mapA[s], sg.A, sg.K, g.Ti, g.B, sg.lda, tc::BK, tc::BM, fp16)) return 1;
+    a.shift[s] = sg.shift;
+    const int K16 = (sg.K + 15) / 16 * 16;
+    a.nchunk[s] = (K16 + tc::BK - 1) / tc::BK;
+    a.last_ksteps[s] = (K16 - (a.nchunk[s] - 1) * tc::BK) / tc::UMMA_K;
+    a.wk0[s] = sg.koff;
+    total_chunks += a.nchunk[s];
+  }
+  int bn;
+  bool ws = false, pair = false;
+  switch (kind) {
+    case EPI_GATE: bn = 256; pair = gate_multicast(); break;
+    case EPI_RES_SKIP: bn = 128; ws = true; FWN_CHECK(total_chunks <= 4, "res|skip GEMM needs K <= 256"); break;
+    case EPI_LINEAR: bn = 128; ws = total_chunks <= 4; break;
+    case EPI_PLAIN: bn = 128; ws = total_chunks <= 4; FWN_CHECK(g.N % 128 == 0, "16-bit PLAIN GEMM needs N %% 128 == 0 (N=%d)", g.N); break;
+    case EPI_PLAIN_F32:
+    case EPI_AFFINE: bn = tc::block_n_for(EPI_AFFINE, g.N, false); break;
+    default: FWN_CHECK(false, "tc_gemm16: unsupported epilogue %d", (int)kind);
+  }
+  // weights [Npad][Kpad]: 2-D map, (64, box_n) box
+  const int box_n = pair ? bn / 2 : std::min(bn, Npad);
+  if (tc_map_3d(&a.mapB, W, Kpad, Npad, 0, Kpad, tc::BK, box_n, fp16)) return 1;
+  auto act = [&](const void* p, CUtensorMap* dst, int C, int rows) { return p ? tc_map_3d(dst, p, C, g.Ti, g.B, C, tc::BK, rows, fp16) : 0; };
+  if (kind == EPI_GATE) {
+    FWN_CHECK(!(fp16 && g.e.tape), "the gate tape is a bf16 training feature");
+    if (act(g.e.out0, &a.mapOut[0], F, 32)) return 1;
+  } else if (kind == EPI_RES_SKIP) {
+    if (g.e.has_res) {
+      if (act(g.e.out0, &a.mapOut[0], F, 32) || act(g.e.in0, &a.mapIn[0], F, tc::BM)) return 1;
+      a.has_in[0] = 1;
+    }
+    if (act(g.e.out1, &a.mapOut[1], F, 32)) return 1;
+    if (g.e.in1) {
+      if (act(g.e.in1, &a.mapIn[1], F, tc::BM)) return 1;
+      a.has_in[1] = 1;
+    }
+  } else if (kind == EPI_LINEAR) {
+    FWN_CHECK(g.N % 128 == 0, "16-bit LINEAR GEMM needs N %% 128 == 0 (N=%d)", g.N);
+    g.e.has_res = 1;      // every column tile takes the "residual" route of the staged epilogue: map 0 in, map 0 out
+    g.e.F = g.N;
+    if (act(g.e.out0, &a.mapOut[0], g.N, 32)) return 1;
+    if (g.e.in0) {
+      if (act(g.e.in0, &a.mapIn[0], g.N, tc::BM)) return 1;
+      a.has_in[0] = 1;
+    }
+  } else if (kind == EPI_PLAIN) {
+    if (act(g.e.out0, &a.mapOut[0], g.N, 32)) return 1;
+  }
+  a.B = g.B;
+  a.Ti = g.Ti;
+  a.tiles_per_utt = (g.Ti + tc::BM - 1) / tc::BM;
+  a.N = g.N;
+  a.n_tiles = (g.N + bn - 1) / bn;
+  a.e = g.e;
+  a.multicast = pair ? 1 : 0;
+  a.fp16 = fp16 ? 1 : 0;
+  return tc::tc_launch(a, kind, bn, ws, st);
 }
 
 void tc_free(Model* m) {

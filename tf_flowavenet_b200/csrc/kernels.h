@@ -37,7 +37,9 @@ struct Seg {
 enum EpiKind { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RES_SKIP = 2, EPI_AFFINE = 3,
                // backward pass (fp32 engines only):
                EPI_LINEAR = 4,    // y = alpha * (acc + bias? + in0?), optionally masked by (in1 > 0)  (dgrad of the 1x1 / dilated convs)
-               EPI_GATE_BWD = 5   // acc = dL/do -> (dL/df, dL/dg) interleaved, from the saved pre-activations (modules.py:124)
+               EPI_GATE_BWD = 5,  // acc = dL/do -> (dL/df, dL/dg) interleaved, from the saved pre-activations (modules.py:124)
+               // 16-bit training mode (tcgen05 engine only):
+               EPI_PLAIN_F32 = 6  // y (fp32, row pitch ld) = acc or y += acc: narrow / accumulating outputs (front-conv dgrad, conditioning gradient)
 };
 
 struct EpiArgs {
@@ -52,6 +54,10 @@ struct EpiArgs {
   int has_res;             // RES_SKIP: columns [0,F) are the residual conv
   int F;                   // filter size
   float alpha;             // LINEAR: output scale
+  // 16-bit training mode (gemm_tc.cu)
+  void* tape;              // GATE: sigmoid(g) [rows, F] saved for the backward pass (with o it determines both gate derivatives)
+  int mask_mode;           // LINEAR: in0 is a ReLU mask (y = in0 > 0 ? alpha acc : 0) instead of an addend (y = alpha (acc + in0))
+  int accum;               // PLAIN_F32: y += acc
   // AFFINE (zero-conv epilogue == ActNorm + coupling in place on the flow variable)
   float* X;                // [rows, Cx] fp32, physical (time-ordered) layout
   int Cx, nq;
@@ -73,6 +79,26 @@ struct GemmArgs {
   int B, Ti;
   EpiArgs e;
 };
+
+// ---- gemm_tc.cu: one 16-bit implicit GEMM on the tcgen05 engine with operands anywhere in device memory (the training step's tape;
+// the inference passes go through the planned workspace of tc_prepare / tc_run).  Tensor maps are cached per (pointer, shape).
+//   kind: GATE (out0 = o, e.tape = sigmoid(g)), RES_SKIP, PLAIN (16-bit out, bias / relu), LINEAR (16-bit out, staged addend or mask),
+//         PLAIN_F32 (fp32 out, optional accumulate), AFFINE (in place on X; e.out1 = (log_s, t) fp32 with row pitch e.ld)
+//   W: 16-bit [Npad][Kpad] K-major (plane 0 of the split engine's operand planes)
+int tc_gemm16(const GemmArgs& g, EpiKind kind, const void* W, int Kpad, int Npad, bool fp16, cudaStream_t st);
+
+// ---- wgrad_tc.cu: dW[koff + k, n] += sum_{b,t} A[b, t + shift, k] dY[b, t, n] with bf16 operands (see the file header)
+struct Wgrad16Args {
+  Seg seg[4];                                  // A operands (bf16), K = channels, koff = first dW row
+  int nseg;
+  const void* dY0; int64_t ld0; int n0cols;    // dY columns [0, n0cols) come from dY0, [n0cols, N) from dY1 (bf16)
+  const void* dY1; int64_t ld1;
+  int N;
+  float* dW; int64_t ldw;                      // [Ktot, ldw] fp32, accumulated with atomics
+  int B, Ti;
+};
+bool wgrad_tc_supported(const Wgrad16Args& a);
+int wgrad_tc(const Wgrad16Args& a, float* dbias, cudaStream_t st);
 
 // ---- conv_simt.cu (fp32 CUDA-core engine)
 int simt_gemm(const GemmArgs& a, EpiKind kind, cudaStream_t st);

@@ -88,6 +88,8 @@ struct Model {
   // fp32 training, parity setting: run the FORWARD GEMMs of the training step on the CUDA-core engine (round-to-nearest FFMA chains).
   // The tensor cores' accumulator truncates, a bias the backward pass amplifies on cancellation-heavy gradients.
   bool train_exact_fwd = false, force_simt = false;
+  // training compute dtype: false = fp32-accurate (split engine), true = bf16 operands / tape on the tcgen05 engine (train16.cu)
+  bool train_bf16 = false;
   bool packed = false, rev_ok = false;
   char* pack = nullptr;
   size_t pack_bytes = 0;

@@ -18,50 +18,6 @@
 
 namespace fwn {
 
-struct TrainFlow {
-  W3 zero_T, final_T, front_T;
-  W3 rs_T[MAX_LAYERS], gate_T[MAX_LAYERS], cond_T[MAX_LAYERS];
-};
-
-struct TrainState {
-  float* what = nullptr;      // [raw + ext] folded parameters
-  int32_t* wmap = nullptr;    // [wall] gather map
-  float* gwall = nullptr;     // [wall] gradients of the packed fp32 operands / bias vectors
-  FoldDesc* d_folds = nullptr;
-  FoldWork* d_fwork = nullptr;
-  int n_fwork = 0;
-  PlaneDesc* d_pdesc = nullptr;
-  PlaneWork* d_pwork = nullptr;
-  int n_pwork = 0;
-  ActnormDesc* d_an = nullptr;
-  char* planes = nullptr;     // transposed bf16x3 planes (dgrad operands)
-  std::vector<TrainFlow> flows;
-  float *adam_m = nullptr, *adam_v = nullptr;
-  double* scratch = nullptr;  // [8]
-  float* norm = nullptr;      // [1]
-  double* up_dw = nullptr;    // [max 2s*3 + 1]
-  // backward pass: weight gradients and the conditioning gradient are off the critical chain of dgrads -> low-priority side stream
-  cudaStream_t side = nullptr;
-  std::vector<cudaEvent_t> ev;
-  size_t ev_next = 0;
-  cudaEvent_t set_done[2] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> cond_ready;   // per block: the conditioning projections of its flows are in the tape
-  // Gradient buckets in PRODUCTION order (block n-1 first, ..., block 0, then the upsampler / speaker-embedding rest): contiguous
-  // ranges of the flat gradient whose values are final once `ready` has fired, so the tower average of bucket k (an all-reduce on
-  // the caller's communication stream, utils.py:34-60) overlaps the backward pass of the blocks still to come.
-  struct Bucket { int64_t off, count; int64_t wall0, wall1; int work0, work1; cudaEvent_t ready; };
-  std::vector<Bucket> buckets;
-  cudaEvent_t next_event() {
-    if (ev.empty()) {
-      ev.resize(64);
-      for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    }
-    cudaEvent_t e = ev[ev_next];
-    ev_next = (ev_next + 1) % ev.size();
-    return e;
-  }
-};
-
 void train_free(Model* m) {
   TrainState* t = m->train;
   if (!t) return;
@@ -328,6 +284,7 @@ static int train_plan(const Model* m, int B, int T, TrainWs* w, char* base) {
   return 0;
 }
 int64_t train_workspace_bytes(const Model* m, int B, int T) {
+  if (m->train_bf16) return train16_workspace_bytes(m, B, T);
   TrainWs w;
   if (train_plan(m, B, T, &w, nullptr)) return -1;
   return (int64_t)w.bytes;
@@ -446,11 +403,61 @@ static int flow_forward(Model* m, const TrainWs& w, const FlowPack& fp, const Ta
 static float* gw(const Model* m, const void* P) {  // gradient slot mirroring a packed fp32 operand / bias vector
   return m->train->gwall + (reinterpret_cast<const float*>(P) - reinterpret_cast<const float*>(m->pack));
 }
+float* train_gw(const Model* m, const void* P) { return gw(m, P); }
 
 // FWN_TRAIN_STREAMS=1 keeps the whole backward pass on the caller's stream (diagnostics / A-B timing)
 static bool dual_stream() {   // read per call: tests flip it between two passes of one process
   const char* e = getenv("FWN_TRAIN_STREAMS");
   return !(e && e[0] == '1');
+}
+bool train_dual_stream() { return dual_stream(); }
+
+// Block `block` is done: packed-operand gradients -> folded vector -> raw variables for THIS block, behind its weight gradients on
+// the side stream (the dgrad chain of the next block does not wait for it); then the block's bucket of the flat gradient is final.
+int train_finish_block(Model* m, int block, float* grads, cudaStream_t st) {
+  TrainState* t = m->train;
+  TrainState::Bucket& bk = t->buckets[(size_t)(m->cfg.n_block - 1 - block)];
+  cudaStream_t s1 = dual_stream() ? t->side : st;
+  if (dual_stream()) {   // the ActNorm gradients of the block were written on the main stream
+    cudaEvent_t e = t->next_event();
+    FWN_CUDA(cudaEventRecord(e, st));
+    FWN_CUDA(cudaStreamWaitEvent(s1, e, 0));
+  }
+  m->launches += 2;
+  if (scatter_grad(t->gwall + bk.wall0, t->wmap + bk.wall0, grads, bk.wall1 - bk.wall0, s1)) return 1;
+  if (fold_backward(m->raw, grads, t->d_folds, t->d_fwork + bk.work0, bk.work1 - bk.work0, m->raw_floats, s1)) return 1;
+  FWN_CUDA(cudaEventRecord(bk.ready, s1));
+  return 0;
+}
+
+// Gradient of the two transposed-conv stages (model.py:398-404) from the accumulated conditioning gradient; closes the flat gradient
+// (records the events of the buckets behind the blocks).  c planes / up0 are the fp32 forward outputs (leaky-relu masks).
+int train_upsampler_backward(Model* m, const float* cmel, const float* up0, float* dup0, const float* cA, const float* cB, const float* dcA,
+                             const float* dcB, int B, int T, float* grads, cudaStream_t st) {
+  const fwn_config& c = m->cfg;
+  TrainState* t = m->train;
+  int Tm = T / m->hop;
+  const int last = c.n_upsample - 1;
+  auto poff = [&](const std::string& n) { return m->params[m->index.at(n)].offset; };
+  auto pname = [&](int i) { return i == 0 ? std::string("conv2d_transpose") : "conv2d_transpose_" + std::to_string(i); };
+  for (int i = last; i >= 0; --i) {
+    const int s = c.upsample_scales[i];
+    int Tin = Tm;
+    for (int k = 0; k < i; ++k) Tin *= c.upsample_scales[k];
+    const float* in = i == 0 ? cmel : up0;
+    const bool split = i == last;
+    const float *d0 = split ? dcA : dup0, *d1 = split ? dcB : nullptr;
+    const float *o0 = split ? cA : up0, *o1 = split ? cB : nullptr;
+    m->launches += 3;
+    if (upsample_bwd_stage(d0, d1, o0, o1, split, in, m->up_w[i], t->up_dw, i > 0 ? dup0 : nullptr, B, Tin, c.num_mels, s, st)) return 1;
+    const std::string n = pname(i);
+    if (upsample_wn_bwd(m->raw + poff(n + "/kernel"), m->raw + poff(n + "/wn/g"), t->up_dw, s, grads + poff(n + "/kernel"),
+                        grads + poff(n + "/wn/g"), grads + poff(n + "/bias"), st))
+      return 1;
+  }
+  // the upsampler variables (and the speaker embeddings, whose gradient is identically zero: SURVEY F6) close the gradient
+  for (size_t k = (size_t)c.n_block; k < t->buckets.size(); ++k) FWN_CUDA(cudaEventRecord(t->buckets[k].ready, st));
+  return 0;
 }
 
 static int flow_backward(Model* m, const TrainWs& w, const FlowPack& fp, const TrainFlow& tf, const Tape& tp, const float* Xpost, int B,
@@ -586,6 +593,7 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   FWN_CHECK(x && cmel && grads, "null pointer");
   FWN_CHECK(!(m->cfg.gin_channels > 0 && gspk == nullptr), "g is None");
   FWN_CHECK(grad_floats >= train_grad_floats(m), "gradient buffer too small: need %lld floats", (long long)train_grad_floats(m));
+  if (m->train_bf16) return train16_loss_and_grads(m, x, cmel, gspk, B, T, logp_out, logdet_out, grads, grad_floats, ws, ws_bytes, st);
   TrainWs w;
   if (train_plan(m, B, T, &w, (char*)ws)) return 1;
   FWN_CHECK(ws && ws_bytes >= (int64_t)w.bytes, "workspace too small: need %lld bytes, got %lld", (long long)w.bytes, (long long)ws_bytes);
@@ -649,19 +657,7 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
       const float* Xpost = f + 1 < m->flows.size() ? w.tape[f + 1].xpre : w.X;
       if (flow_backward(m, w, m->flows[f], t->flows[f], w.tape[f], Xpost, B, T >> (i + 1), grads, (int)(f & 1), st)) return 1;
     }
-    // Block i is done: packed-operand gradients -> folded vector -> raw variables for THIS block, behind its weight gradients on
-    // the side stream (the dgrad chain of the next block does not wait for it); then the block's bucket of the flat gradient is final.
-    TrainState::Bucket& bk = t->buckets[(size_t)(c.n_block - 1 - i)];
-    cudaStream_t s1 = dual_stream() ? t->side : st;
-    if (dual_stream()) {   // the ActNorm gradients of the block were written on the main stream
-      cudaEvent_t e = t->next_event();
-      FWN_CUDA(cudaEventRecord(e, st));
-      FWN_CUDA(cudaStreamWaitEvent(s1, e, 0));
-    }
-    m->launches += 2;
-    if (scatter_grad(t->gwall + bk.wall0, t->wmap + bk.wall0, grads, bk.wall1 - bk.wall0, s1)) return 1;
-    if (fold_backward(m->raw, grads, t->d_folds, t->d_fwork + bk.work0, bk.work1 - bk.work0, m->raw_floats, s1)) return 1;
-    FWN_CUDA(cudaEventRecord(bk.ready, s1));
+    if (train_finish_block(m, i, grads, st)) return 1;
   }
   if (dual_stream()) {   // join: the conditioning gradient and all weight gradients are complete
     cudaEvent_t e = t->next_event();
@@ -669,30 +665,7 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
     FWN_CUDA(cudaStreamWaitEvent(st, e, 0));
   }
   // ---- upsampler
-  {
-    int Tm = T / m->hop;
-    const int last = c.n_upsample - 1;
-    auto poff = [&](const std::string& n) { return m->params[m->index.at(n)].offset; };
-    auto pname = [&](int i) { return i == 0 ? std::string("conv2d_transpose") : "conv2d_transpose_" + std::to_string(i); };
-    for (int i = last; i >= 0; --i) {
-      const int s = c.upsample_scales[i];
-      int Tin = Tm;
-      for (int k = 0; k < i; ++k) Tin *= c.upsample_scales[k];
-      const float* in = i == 0 ? cmel : w.up0;
-      const bool split = i == last;
-      const float *d0 = split ? w.dcA : w.dup0, *d1 = split ? w.dcB : nullptr;
-      const float *o0 = split ? w.cA : w.up0, *o1 = split ? w.cB : nullptr;
-      m->launches += 3;
-      if (upsample_bwd_stage(d0, d1, o0, o1, split, in, m->up_w[i], t->up_dw, i > 0 ? w.dup0 : nullptr, B, Tin, c.num_mels, s, st)) return 1;
-      const std::string n = pname(i);
-      if (upsample_wn_bwd(m->raw + poff(n + "/kernel"), m->raw + poff(n + "/wn/g"), t->up_dw, s, grads + poff(n + "/kernel"),
-                          grads + poff(n + "/wn/g"), grads + poff(n + "/bias"), st))
-        return 1;
-    }
-  }
-  // the upsampler variables (and the speaker embeddings, whose gradient is identically zero: SURVEY F6) close the gradient
-  for (size_t k = (size_t)c.n_block; k < t->buckets.size(); ++k) FWN_CUDA(cudaEventRecord(t->buckets[k].ready, st));
-  return 0;
+  return train_upsampler_backward(m, cmel, w.up0, w.dup0, w.cA, w.cB, w.dcA, w.dcB, B, T, grads, st);
 }
 
 int train_bucket_count(const Model* m) { return m->train ? (int)m->train->buckets.size() : -1; }

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <vector>
+
 #include "model.h"
 
 namespace fwn {
@@ -34,6 +36,51 @@ struct WgradArgs {
   float* dW; int64_t ldw;                      // [Ktot, ldw] fp32, accumulated with atomics
   int B, Ti;
   int slabs_per_utt;                           // set by wgrad()
+};
+
+// ---- training state (train.cu builds it; train16.cu, the 16-bit mode, shares it)
+struct TrainFlow {
+  W3 zero_T, final_T, front_T;
+  W3 rs_T[MAX_LAYERS], gate_T[MAX_LAYERS], cond_T[MAX_LAYERS];
+};
+
+struct TrainState {
+  float* what = nullptr;      // [raw + ext] folded parameters
+  int32_t* wmap = nullptr;    // [wall] gather map
+  float* gwall = nullptr;     // [wall] gradients of the packed fp32 operands / bias vectors
+  FoldDesc* d_folds = nullptr;
+  FoldWork* d_fwork = nullptr;
+  int n_fwork = 0;
+  PlaneDesc* d_pdesc = nullptr;
+  PlaneWork* d_pwork = nullptr;
+  int n_pwork = 0;
+  ActnormDesc* d_an = nullptr;
+  char* planes = nullptr;     // transposed bf16x3 planes (dgrad operands)
+  std::vector<TrainFlow> flows;
+  float *adam_m = nullptr, *adam_v = nullptr;
+  double* scratch = nullptr;  // [8]
+  float* norm = nullptr;      // [1]
+  double* up_dw = nullptr;    // [max 2s*3 + 1]
+  // backward pass: weight gradients and the conditioning gradient are off the critical chain of dgrads -> low-priority side stream
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_next = 0;
+  cudaEvent_t set_done[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> cond_ready;   // per block: the conditioning projections of its flows are in the tape
+  // Gradient buckets in PRODUCTION order (block n-1 first, ..., block 0, then the upsampler / speaker-embedding rest): contiguous
+  // ranges of the flat gradient whose values are final once `ready` has fired, so the tower average of bucket k (an all-reduce on
+  // the caller's communication stream, utils.py:34-60) overlaps the backward pass of the blocks still to come.
+  struct Bucket { int64_t off, count; int64_t wall0, wall1; int work0, work1; cudaEvent_t ready; };
+  std::vector<Bucket> buckets;
+  cudaEvent_t next_event() {
+    if (ev.empty()) {
+      ev.resize(64);
+      for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    cudaEvent_t e = ev[ev_next];
+    ev_next = (ev_next + 1) % ev.size();
+    return e;
+  }
 };
 
 // ---- train_kernels.cu
@@ -70,6 +117,23 @@ int tc3_gemm(const GemmArgs& g, EpiKind kind, const void* w3, int Kpad, int Npad
 // ---- model.cu helpers shared with the training pass
 int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, int T, cudaStream_t st);
 int finish_forward(const double* sums, const double* an_logdet, float* logp_out, float* logdet_out, double n, cudaStream_t st);
+
+// ---- train_kernels16.cu (bf16 tape / gradients)
+int affine_bwd16(float* dX, const float* Xpost, const float* net, int64_t ldn, void* dNet, int64_t ldd, int64_t rows, int Cx, int nq,
+                 const int* b_off, double n_total, cudaStream_t st);
+int gate_bwd16(const void* dO, const void* O, const void* S, void* dFG, int64_t n, cudaStream_t st);
+int relu_mask16(void* Y, const void* H, int64_t n, cudaStream_t st);
+
+// ---- train16.cu: the training step with bf16 operands / tape on the tcgen05 engine (fp32 master variables, fp32 accumulation)
+int64_t train16_workspace_bytes(const Model* m, int B, int T);
+int train16_loss_and_grads(Model* m, const float* x, const float* c, const int32_t* g, int B, int T, float* logp_out, float* logdet_out,
+                           float* grads, int64_t grad_floats, void* ws, int64_t ws_bytes, cudaStream_t st);
+// shared pieces of the two modes (train.cu)
+float* train_gw(const Model* m, const void* P);        // gradient slot mirroring a packed fp32 operand / bias vector
+bool train_dual_stream();
+int train_finish_block(Model* m, int block, float* grads, cudaStream_t st);   // scatter + unfold of one block, bucket event
+int train_upsampler_backward(Model* m, const float* cmel, const float* up0, float* dup0, const float* cA, const float* cB, const float* dcA,
+                             const float* dcB, int B, int T, float* grads, cudaStream_t st);
 
 // ---- train.cu
 int train_enable(Model* m, cudaStream_t st);

@@ -105,7 +105,8 @@ class Trainer:
                  exact_forward=None, overlap_allreduce=True):
         """model: an fp32 FloWaveNet (fp32 master variables, as utils.fp16_dtype_getter keeps them, utils.py:3-31).
         compute_dtype: 'float32' = fp32-accurate GEMMs (3-way bf16 split on the tensor cores; `split_terms` products per fp32 product:
-        6 = every product down to 2^-24, 3 = ~2^-16 at half the tensor work).
+        6 = every product down to 2^-24, 3 = ~2^-16 at half the tensor work); 'bfloat16' = bf16 operands and tape with fp32
+        accumulation, reductions and gradients (the reference's mixed-precision training, utils.py:3-31, with bf16 for fp16).
         exact_forward (fp32 only; default: on for split_terms=6): forward GEMMs of the step on the CUDA-core engine -- the parity
         setting that keeps EVERY variable's gradient within 2e-4 of its own max-abs (see fwn_set_train_exact_forward).
         The static loss scale of the reference (hparams.scale = 64, train.py:62,75-77) exists for fp16 gradients; every mode here
@@ -113,8 +114,8 @@ class Trainer:
         if model._precision != _lib.FWN_FP32:
             raise ValueError("training keeps fp32 master variables: build the model with hparams.dtype='float32' and choose the "
                              "compute dtype with Trainer(compute_dtype=...)")
-        if compute_dtype not in ("float32",):
-            raise ValueError("unsupported compute_dtype %r" % (compute_dtype,))
+        if compute_dtype not in ("float32", "bfloat16"):
+            raise ValueError("unsupported compute_dtype %r (float32 or bfloat16)" % (compute_dtype,))
         self.model, self.group = model, group
         self.clip_norm, self.beta1, self.beta2, self.epsilon = clip_norm, beta1, beta2, epsilon
         self.compute_dtype = compute_dtype
@@ -124,8 +125,9 @@ class Trainer:
         with torch.cuda.device(model._device):
             _lib.check(L.fwn_train_enable(model._h, _lib.stream_ptr()))
         _lib.check(L.fwn_set_split_terms(model._h, 6, int(split_terms)))
-        self.exact_forward = bool(split_terms == 6) if exact_forward is None else bool(exact_forward)
+        self.exact_forward = bool(split_terms == 6 and compute_dtype == "float32") if exact_forward is None else bool(exact_forward)
         _lib.check(L.fwn_set_train_exact_forward(model._h, int(self.exact_forward)))
+        _lib.check(L.fwn_set_train_compute(model._h, _lib.FWN_MIXED_BF16 if compute_dtype == "bfloat16" else _lib.FWN_FP32))
         self._n = L.fwn_grad_floats(model._h)
         self._np = L.fwn_param_floats(model._h)
         self.grads = torch.zeros(self._n, dtype=torch.float32, device=model._device)
