@@ -182,3 +182,14 @@ def test_synthesis_caller_npy_to_wav(tmp_path):
     # and against the oracle on the same z (fp32 tolerance of BASELINE: 1e-3 max-abs)
     ref = O.reverse(params, hp, torch.from_numpy(z0), torch.from_numpy(mel0[None]), torch.float64).numpy().reshape(-1)
     assert np.abs(want - ref).max() < 1e-3
+    # --saved_dir, the reference's own flag (synthesize.py:28-34): a tf.train.Saver checkpoint directory read without TensorFlow --
+    # variables under vocoder/FloWaveNet/ next to Adam slots and global_step -- gives the same wavs as the .npz
+    from tf_flowavenet_b200 import checkpoint as C
+    ckpt = {"vocoder/FloWaveNet/" + k: v.numpy() for k, v in params.items()}
+    ckpt.update({"vocoder/FloWaveNet/" + k + "/Adam": np.zeros_like(v.numpy()) for k, v in params.items()})
+    ckpt["global_step"] = np.array(500000, dtype=np.int64)
+    C.write_checkpoint(str(tmp_path / "logs" / "model.ckpt-500000"), ckpt)
+    out2 = tmp_path / "out2"
+    S.synthesize(types.SimpleNamespace(saved_dir=str(tmp_path / "logs"), weights=None, mels_dir=str(mels), output_dir=str(out2), seed=5), hparams)
+    for n in ("utt0.wav", "utt1.wav"):
+        assert open(out / n, "rb").read() == open(out2 / n, "rb").read()

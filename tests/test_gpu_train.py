@@ -296,6 +296,30 @@ def test_dataset_feeds_trainer(tmp_path):
     assert all(np.isfinite(losses)) and tr.global_step == 4
 
 
+def test_tf_checkpoint_save_restore(tmp_path):
+    """Trainer.save_checkpoint writes tf.train.Saver's TensorBundle format (train.py:190,252); restoring it into a fresh trainer
+    continues the run, and the model variables in it are what synthesize --saved_dir loads."""
+    import tf_flowavenet_b200.train as T
+    from tf_flowavenet_b200 import checkpoint as C
+    hp, params, fx = load("g1_b2f2l2")
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    tr = T.Trainer(make_model(hp, params))
+    for _ in range(2):
+        tr.train_step(x, c)
+    prefix = tr.save_checkpoint(str(tmp_path / "logs" / "model.ckpt-2"))
+    ck = C.load_checkpoint(prefix)
+    assert int(ck["global_step"]) == 2 and "vocoder/FloWaveNet/Block_0/Flow_0/ActNorm/logs/Adam_1" in ck
+    live = tr.variables()
+    for k, v in C.flowavenet_variables(C.latest_checkpoint(str(tmp_path / "logs"))).items():
+        np.testing.assert_array_equal(v, live[k].cpu().numpy())
+    a = tr.train_step(x, c)
+    tr2 = T.Trainer(make_model(hp, params))
+    tr2.restore_checkpoint(prefix)
+    assert tr2.global_step == 2
+    b = tr2.train_step(x, c)
+    assert abs(float(a["loss"]) - float(b["loss"])) < 1e-5 * max(1.0, abs(float(a["loss"])))
+
+
 def test_checkpoint_resume_continues_the_same_trajectory():
     """train.py:190,199-210: saving variables + Adam slots + step and restoring them into a fresh trainer continues bit-compatibly
     (up to the order of fp32 atomics in the weight gradients)."""

@@ -17,6 +17,7 @@
 // accumulator stage and one staging buffer, so the latency chains of two consecutive tiles overlap.  Tiles move through
 // 128B-swizzled shared memory: residual / skip inputs arrive by TMA bulk loads, outputs leave by per-warp TMA bulk stores.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <unordered_map>
@@ -87,7 +88,7 @@ struct Cfg {
   // TMEM accumulator stages: 4 where they fit (BN <= 128) so the MMA warp can run several tiles ahead of the epilogue groups
   static constexpr int NACC = (BN <= 128) ? 4 : 2;
   static constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + BIAS_BYTES + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)W_BYTES + (size_t)NSTG * STG_BYTES + BIAS_BYTES + 320;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -124,7 +125,6 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
   if (EPI == EPI_GATE) {
     // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124); 16 columns -> 8 channels = one 16-byte chunk
     uint32_t p[4];
-#pragma unroll
     if (fp16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -304,10 +304,14 @@ __device__ __forceinline__ void affine16_regs(const EpiArgs& e, const float* sbi
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int EPI, int BN, bool WS, bool PAIR>
+// CL > 1 (weight-stationary kernels only): the CL CTAs of a cluster own the CL column tiles of the SAME row tiles.  Their A operand
+// is identical, so the leader fetches every activation chunk once and TMA-multicasts it into all CL shared memories: L2->SM
+// activation traffic drops by CL (the K = 256 GEMMs re-read their A tile once per column tile and were bound by the L2 fabric).
+template <int EPI, int BN, bool WS, bool PAIR, int CL = 1>
 __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_kernel(const __grid_constant__ TcArgs a) {
   using C = Cfg<EPI, BN, WS, PAIR>;
   static_assert(!(WS && PAIR), "the CTA-pair variant is for the streaming kernel");
+  static_assert(CL == 1 || WS, "activation multicast is for the weight-stationary kernels");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -321,7 +325,8 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   uint64_t* in_full = tmem_empty + 4;   // staged inputs landed (RES_SKIP)
   uint64_t* in_empty = in_full + 3;     // staging buffer may be overwritten by the next input load
   uint64_t* w_full = in_empty + 3;      // WS: resident weights landed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* cl_empty = w_full + 1;      // CL > 1, leader: every CTA of the cluster has freed the stage and expects the next chunk
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cl_empty + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_tiles = a.B * a.tiles_per_utt;
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   const int ws_groups = WS ? (int)gridDim.x / a.n_tiles : 1;
   const int ws_n = WS ? (int)blockIdx.x % a.n_tiles : 0;
   const int ws_m0 = WS ? (int)blockIdx.x / a.n_tiles : 0;
-  const int mc_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int mc_rank = (PAIR || CL > 1) ? (int)cluster_ctarank() : 0;
   const bool leader = mc_rank == 0;
   auto tile_of = [&](int it, int& m_tile, int& n_tile) -> bool {
     if (PAIR) {  // cluster c handles row-tile pairs; an odd tail pair's second tile is a dummy (TMA zero fill in, clipped out)
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
       mbar_init(in_empty + i, 4);   // the four warps of the group that stored from this staging buffer
     }
     mbar_init(w_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(cl_empty + i, CL);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < C::BIAS_BYTES / 4; i += C::THREADS) {
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();  // peer barriers are initialised before any remote arrive
+  if (PAIR || CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // the next kernel of the chain may be scheduled as SMs free up (its own prologue overlaps our tail) ...
@@ -435,6 +441,14 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
               if (leader) mbar_expect_tx(full_bar + stage, 2 * C::STAGE_BYTES);
               tma_load_3d_2sm(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
               tma_load_2d_2sm(sa + A_BYTES, &a.mapB, full_bar + stage, a.wk0[s] + ch * BK, n_tile * BN + mc_rank * (BN / 2));
+            } else if (CL > 1) {
+              // this CTA's stage is free (waited above) and now expects the chunk; once all CL CTAs said so, the leader multicasts it
+              mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
+              mbar_arrive_remote(cl_empty + stage, 0);
+              if (leader) {
+                mbar_wait(cl_empty + stage, phase);
+                tma_load_3d_mc(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub, (uint16_t)((1u << CL) - 1));
+              }
             } else {
               mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
               tma_load_3d(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
@@ -600,7 +614,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer's MMAs / arrives may still target it
+  if (PAIR || CL > 1) cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer's MMAs / arrives / multicasts may still target it
   if (warp == 1) {
     tcgen05_fence_after();
     if (PAIR) tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
@@ -666,12 +680,40 @@ int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
   return 0;
 }
 
-template <int EPI, int BN, bool WS, bool PAIR = false>
+// FWN_WS_MULTICAST=0 runs the weight-stationary GEMMs without cluster multicast of the activation chunks (diagnostics / A-B timing)
+static bool ws_multicast() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_WS_MULTICAST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int EPI, int BN, bool WS, bool PAIR = false, int CL = 1>
 static int launch(const TcArgs& a, cudaStream_t st) {
   using C = Cfg<EPI, BN, WS, PAIR>;
   static bool configured = false;
+  static int max_clusters = 0;   // CL > 1: clusters of CL CTAs that can be resident at once
   if (!configured) {
-    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, WS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    FWN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, BN, WS, PAIR, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    if (CL > 1) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3((unsigned)(num_sms() / CL * CL));
+      q.blockDim = dim3(C::THREADS);
+      q.dynamicSmemBytes = C::SMEM;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_gemm_kernel<EPI, BN, WS, PAIR, CL>, &q) != cudaSuccess || max_clusters <= 0) {
+        cudaGetLastError();
+        max_clusters = num_sms() / CL;
+      }
+    }
     configured = true;
   }
   const int num_m = a.B * a.tiles_per_utt;
@@ -680,7 +722,9 @@ static int launch(const TcArgs& a, cudaStream_t st) {
     int nch = 0;
     for (int s = 0; s < a.nseg; ++s) nch += a.nchunk[s];
     FWN_CHECK(nch <= C::WS_CHUNKS, "weight-stationary GEMM needs K <= 256");
-    const int groups = std::max(1, std::min(num_m, num_sms() / a.n_tiles));
+    FWN_CHECK(CL == 1 || CL == a.n_tiles, "internal: cluster size must equal the number of column tiles");
+    const int cap = CL > 1 ? std::min(max_clusters, num_sms() / CL) : num_sms() / a.n_tiles;
+    const int groups = std::max(1, std::min(num_m, cap));
     grid = groups * a.n_tiles;
   } else if (PAIR) {
     const int pairs = ((num_m + 1) / 2) * a.n_tiles;
@@ -695,9 +739,9 @@ static int launch(const TcArgs& a, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (PAIR) {
+  if (PAIR || CL > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.x = PAIR ? 2 : CL;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -709,7 +753,7 @@ static int launch(const TcArgs& a, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  FWN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, WS, PAIR>, a));
+  FWN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, BN, WS, PAIR, CL>, a));
   FWN_LAUNCH_CHECK();
   return 0;
 }
@@ -729,6 +773,7 @@ int tc_launch(TcArgs& a, EpiKind kind, int bn, bool ws, cudaStream_t st) {
   switch (kind) {
     case EPI_LINEAR:
       FWN_CHECK(bn == 128, "linear runs at BN=128");
+      if (ws && a.n_tiles == 2 && ws_multicast()) return launch<EPI_LINEAR, 128, true, false, 2>(a, st);
       return ws ? launch<EPI_LINEAR, 128, true>(a, st) : launch<EPI_LINEAR, 128, false>(a, st);
     case EPI_PLAIN_F32:
       switch (bn) {
@@ -742,9 +787,18 @@ int tc_launch(TcArgs& a, EpiKind kind, int bn, bool ws, cudaStream_t st) {
     case EPI_GATE:
       FWN_CHECK(bn == 256, "gate needs BN=256");
       return a.multicast ? launch<EPI_GATE, 256, false, true>(a, st) : launch<EPI_GATE, 256, false, false>(a, st);
-    case EPI_RES_SKIP: FWN_CHECK(bn == 128 && ws, "res/skip runs weight-stationary at BN=128"); return launch<EPI_RES_SKIP, 128, true>(a, st);
+    case EPI_RES_SKIP:
+      FWN_CHECK(bn == 128 && ws, "res/skip runs weight-stationary at BN=128");
+      // the column tiles of one row tile share their A operand: clusters of n_tiles CTAs receive it by TMA multicast
+      if (a.n_tiles == 4 && ws_multicast()) return launch<EPI_RES_SKIP, 128, true, false, 4>(a, st);
+      if (a.n_tiles == 2 && ws_multicast()) return launch<EPI_RES_SKIP, 128, true, false, 2>(a, st);
+      return launch<EPI_RES_SKIP, 128, true>(a, st);
     case EPI_PLAIN:
-      if (ws) { FWN_CHECK(bn == 128, "weight-stationary plain GEMM needs BN=128"); return launch<EPI_PLAIN, 128, true>(a, st); }
+      if (ws) {
+        FWN_CHECK(bn == 128, "weight-stationary plain GEMM needs BN=128");
+        if (a.n_tiles == 2 && ws_multicast()) return launch<EPI_PLAIN, 128, true, false, 2>(a, st);
+        return launch<EPI_PLAIN, 128, true>(a, st);
+      }
       switch (bn) {
         case 16: return launch<EPI_PLAIN, 16, false>(a, st);
         case 32: return launch<EPI_PLAIN, 32, false>(a, st);
@@ -1026,8 +1080,9 @@ int tc_gemm16(const GemmArgs& g0, EpiKind kind, const void* W, int Kpad, int Npa
     case EPI_AFFINE: bn = tc::block_n_for(EPI_AFFINE, g.N, false); break;
     default: FWN_CHECK(false, "tc_gemm16: unsupported epilogue %d", (int)kind);
   }
-  // weights [Npad][Kpad]: 2-D map, (64, box_n) box
-  const int box_n = pair ? bn / 2 : std::min(bn, Npad);
+  // weights [Npad][Kpad]: 2-D map, (64, box_n) box.  The box is always the full column tile: the kernel expects BN x 128 bytes per
+  // chunk on its barrier, and rows past Npad are zero-filled by TMA (they still count towards the transaction bytes)
+  const int box_n = pair ? bn / 2 : bn;
   if (tc_map_3d(&a.mapB, W, Kpad, Npad, 0, Kpad, tc::BK, box_n, fp16)) return 1;
   auto act = [&](const void* p, CUtensorMap* dst, int C, int rows) { return p ? tc_map_3d(dst, p, C, g.Ti, g.B, C, tc::BK, rows, fp16) : 0; };
   if (kind == EPI_GATE) {
@@ -1063,6 +1118,14 @@ int tc_gemm16(const GemmArgs& g0, EpiKind kind, const void* W, int Kpad, int Npa
   a.e = g.e;
   a.multicast = pair ? 1 : 0;
   a.fp16 = fp16 ? 1 : 0;
+  if (getenv("FWN_TRACE")) {
+    fprintf(stderr, "tc_gemm16 kind=%d B=%d Ti=%d N=%d bn=%d ws=%d pair=%d Kpad=%d Npad=%d nseg=%d:", (int)kind, g.B, g.Ti, g.N, bn, (int)ws, (int)pair,
+            Kpad, Npad, g.nseg);
+    for (int s = 0; s < g.nseg; ++s)
+      fprintf(stderr, " [K=%d lda=%lld sh=%d koff=%d nch=%d]", g.seg[s].K, (long long)g.seg[s].lda, g.seg[s].shift, g.seg[s].koff, a.nchunk[s]);
+    fprintf(stderr, "\n");
+    fflush(stderr);
+  }
   return tc::tc_launch(a, kind, bn, ws, st);
 }
 

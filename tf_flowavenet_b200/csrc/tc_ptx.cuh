@@ -60,6 +60,15 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// Multicast load: ONE request fetches the box from L2 and writes it to the same shared-memory offset of every CTA in `cta_mask`
+// of the cluster, signalling complete_tx on the barrier at the same offset in each of them (each CTA posts its own expect_tx).
+__device__ __forceinline__ void tma_load_3d_mc(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
 // ---- CTA-pair (cta_group::2) variants.  Both CTAs issue their own loads into their own shared memory, but the
 // transaction bytes complete on the LEADER's (even CTA's) barrier: clearing bit 24 of a shared::cluster address selects
 // the even CTA of the pair at the same offset.

@@ -251,6 +251,12 @@ int wgrad_tc(const Wgrad16Args& w, float* dbias, cudaStream_t st) {
   slabs = std::max<int64_t>(1, std::min<int64_t>(slabs, total_chunks / 4));          // >= 4 chunks per slab: the atomics stay amortised
   a.slabs = (int)slabs;
   FWN_CHECK(slabs <= 65535 && ntiles <= 65535, "wgrad: grid too large");
+  if (getenv("FWN_TRACE")) {
+    fprintf(stderr, "wgrad_tc B=%d Ti=%d N=%d n0=%d ktiles=%d ntiles=%d slabs=%d bias=%d:", w.B, w.Ti, w.N, n0cols, ktiles, ntiles, (int)slabs, dbias != nullptr);
+    for (int s = 0; s < w.nseg; ++s) fprintf(stderr, " [K=%d lda=%lld sh=%d koff=%d]", w.seg[s].K, (long long)w.seg[s].lda, w.seg[s].shift, w.seg[s].koff);
+    fprintf(stderr, "\n");
+    fflush(stderr);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)ktiles, (unsigned)ntiles, (unsigned)slabs);
   cfg.blockDim = dim3(wg16::THREADS);

@@ -248,6 +248,51 @@ class Trainer:
                 _lib.check(L.fwn_set_train_state(m._h, which, _lib.ptr(t), t.numel(), _lib.stream_ptr()))
         self.global_step = int(state["global_step"])
 
+    def save_checkpoint(self, prefix, scope="vocoder/FloWaveNet"):
+        """tf.train.Saver.save (train.py:190,252) in TensorFlow's own file format (checkpoint.py, no TensorFlow needed): the variables
+        under `scope`, their Adam slots ('<name>/Adam', '<name>/Adam_1'), beta powers and global_step.  The reference's
+        synthesize.py / train.py restore (and tf_flowavenet_b200.synthesize --saved_dir) read it back."""
+        from . import checkpoint
+        m, out = self.model, {}
+        state = self.state_dict()
+        flat = {k: state[k].cpu().numpy() for k in ("variables", "adam_m", "adam_v")}
+        L = _lib.lib()
+        for i, (k, shp) in enumerate(m.variable_shapes().items()):
+            off = L.fwn_param_offset(m._h, i)
+            n = 1
+            for s in shp:
+                n *= s
+            name = scope + "/" + k
+            out[name] = flat["variables"][off:off + n].reshape(shp)
+            out[name + "/Adam"] = flat["adam_m"][off:off + n].reshape(shp)
+            out[name + "/Adam_1"] = flat["adam_v"][off:off + n].reshape(shp)
+        import numpy as np
+        out["global_step"] = np.array(self.global_step, dtype=np.int64)
+        out["beta1_power"] = np.array(self.beta1 ** self.global_step, dtype=np.float32)
+        out["beta2_power"] = np.array(self.beta2 ** self.global_step, dtype=np.float32)
+        return checkpoint.write_checkpoint(prefix, out)
+
+    def restore_checkpoint(self, prefix, scope="vocoder/FloWaveNet"):
+        """Saver.restore (train.py:211-219): variables, Adam slots and the step counter from a TensorBundle checkpoint -- one written by
+        save_checkpoint or by the reference's own training run."""
+        import numpy as np
+        from . import checkpoint
+        m, L = self.model, _lib.lib()
+        ck = checkpoint.load_checkpoint(prefix)
+        flat = {k: np.zeros(self._np, dtype=np.float32) for k in ("variables", "adam_m", "adam_v")}
+        for i, (k, shp) in enumerate(m.variable_shapes().items()):
+            off = L.fwn_param_offset(m._h, i)
+            name = scope + "/" + k
+            if name not in ck:
+                raise KeyError("checkpoint %s has no variable '%s'" % (prefix, name))
+            for key, suffix in (("variables", ""), ("adam_m", "/Adam"), ("adam_v", "/Adam_1")):
+                if name + suffix in ck:     # the reference creates no Adam slot for variables without a gradient (speaker embeddings)
+                    a = np.asarray(ck[name + suffix], dtype=np.float32).reshape(-1)
+                    flat[key][off:off + a.size] = a
+        state = {k: torch.from_numpy(v) for k, v in flat.items()}
+        state["global_step"] = int(ck["global_step"]) if "global_step" in ck else 0
+        self.load_state_dict(state)
+
     def gradients(self):
         """{variable name -> view of the flat gradient}."""
         m, L, out = self.model, _lib.lib(), {}
