@@ -124,6 +124,14 @@ __device__ __forceinline__ void epilogue16(const TcArgs& a, int64_t row, bool ro
   }
   if (EPI == EPI_GATE) {
     // (2c, 2c+1) = (filter_c, gate_c): o = tanh(f) * sigmoid(g)   (modules.py:124); 16 columns -> 8 channels = one 16-byte chunk
+    if (e.in0 && row_ok) {   // deep blocks: the conditioning projection of this layer was computed ahead (fp32 [rows, ld])
+      const float4* pp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.in0) + row * e.ld + col);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 q = __ldg(pp + k);
+        acc[4 * k] += q.x; acc[4 * k + 1] += q.y; acc[4 * k + 2] += q.z; acc[4 * k + 3] += q.w;
+      }
+    }
     uint32_t p[4];
     if (fp16) {
 #pragma unroll
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__((Cfg<EPI, BN, WS, PAIR>::THREADS), 1) tc_gemm_
       mbar_wait(w_full, 0);
       tcgen05_fence_after();
     }
-    for (int it = 0; leader && tile_of(it, m_tile, n_tile); ++it) {   // in a pair only the leader CTA issues MMAs
+    for (int it = 0; (!PAIR || leader) && tile_of(it, m_tile, n_tile); ++it) {   // in a cta_group::2 pair only the leader CTA issues MMAs
       mbar_wait(tmem_empty + as, aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);

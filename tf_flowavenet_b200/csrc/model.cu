@@ -358,6 +358,8 @@ int model_prepack(Model* m, cudaStream_t st) {
     W3Off w3[GEMM_IDS];
   };
   std::vector<FlowOff> offs;
+  struct CondOff { int block, half; size_t off; int N, Kpad, Kc; };
+  std::vector<CondOff> cond_offs;
   m->flows.clear();
   double an_logdet = 0.0;
 
@@ -396,6 +398,21 @@ int model_prepack(Model* m, cudaStream_t st) {
     c_map.swap(nc);
     cx *= 2;
     const int nq = cx / 2, Kc = H * cx;
+    // conditioning-ahead operands of a deep block (mixed modes): one [slices * 2F][Kpad] matrix per mel half, filled flow by flow
+    const bool ahead = bf16 != 0 && Kc >= AHEAD_MIN_KC;
+    const int ca_kpad = (Kc + 63) / 64 * 64;
+    size_t ca_off[2] = {0, 0};
+    int ca_used[2] = {0, 0};
+    if (ahead) {
+      const int half0 = c_map[0].m / H;
+      int cnt[2] = {0, 0};
+      for (int j = 0; j < c.n_flow; ++j) cnt[(half0 + j) & 1]++;
+      for (int h = 0; h < 2; ++h) {
+        const size_t bytes = (size_t)cnt[h] * L * 2 * F * ca_kpad * 2;
+        ca_off[h] = b.alloc(std::max<size_t>(bytes, 16));
+        cond_offs.push_back(CondOff{i, h, ca_off[h], cnt[h] * L * 2 * F, ca_kpad, Kc});
+      }
+    }
     for (int j = 0; j < c.n_flow; ++j) {
       FlowPack fp;
       FlowOff fo;
@@ -449,6 +466,9 @@ int model_prepack(Model* m, cudaStream_t st) {
         cpos[l] = c_map[l].o * H + (c_map[l].m % H);
       }
       fp.cond_half = half;
+      fp.ahead = ahead ? 1 : 0;
+      fp.ahead_slot = ca_used[half];
+      if (ahead) ca_used[half] += L;
       // front conv [3][nq][F] (input channel q = logical channel q of x_a)
       {
         Ref w = wn_kernel(hp, wpre + "/Conv_front/conv1d", 3, nq, F);
@@ -481,18 +501,28 @@ int model_prepack(Model* m, cudaStream_t st) {
         Ref wf = wn_kernel(hp, r + "/Conv_filter/conv1d", 3, F, F), wg = wn_kernel(hp, r + "/Conv_gate/conv1d", 3, F, F);
         Ref wcf = wn_kernel(hp, r + "/conv1d", 1, Kc, F), wcg = wn_kernel(hp, r + "/conv1d_1", 1, Kc, F);
         const int Kc16 = (Kc + 15) / 16 * 16;
-        const int Kg = 3 * F + Kc16, Ng = 2 * F;
+        const int Kg = ahead ? 3 * F : 3 * F + Kc16, Ng = 2 * F;   // ahead: the conditioning rows live in the block's cond_w instead
         PMat W((size_t)Kg * Ng), B(Ng);
         for (int k = 0; k < 3 * F; ++k)
           for (int ch = 0; ch < F; ++ch) {
             W[(size_t)k * Ng + 2 * ch] = wf[(size_t)k * F + ch];
             W[(size_t)k * Ng + 2 * ch + 1] = wg[(size_t)k * F + ch];
           }
-        for (int l = 0; l < Kc; ++l)
-          for (int ch = 0; ch < F; ++ch) {
-            W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch] = wcf[(size_t)l * F + ch];
-            W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch + 1] = wcg[(size_t)l * F + ch];
-          }
+        if (!ahead) {
+          for (int l = 0; l < Kc; ++l)
+            for (int ch = 0; ch < F; ++ch) {
+              W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch] = wcf[(size_t)l * F + ch];
+              W[(size_t)(3 * F + cpos[l]) * Ng + 2 * ch + 1] = wcg[(size_t)l * F + ch];
+            }
+        } else {   // rows (slot * 2F + column) of the block's projection operand, K = physical conditioning channel
+          uint16_t* dst = reinterpret_cast<uint16_t*>(b.buf.data() + ca_off[half]) + (size_t)(fp.ahead_slot + n) * 2 * F * ca_kpad;
+          for (int l = 0; l < Kc; ++l)
+            for (int ch = 0; ch < F; ++ch) {
+              const float vf = (float)wcf[(size_t)l * F + ch].v, vg = (float)wcg[(size_t)l * F + ch].v;
+              dst[(size_t)(2 * ch) * ca_kpad + cpos[l]] = bf16 == 2 ? f2h(vf) : f2bf(vf);
+              dst[(size_t)(2 * ch + 1) * ca_kpad + cpos[l]] = bf16 == 2 ? f2h(vg) : f2bf(vg);
+            }
+        }
         // bias of a gate column = conv bias + conditioning-conv bias: an `ext` slot of the folded vector (FOLD_SUM2)
         Ref bfs = hp.ext(r + "/Conv_filter/conv1d/bias"), bgs = hp.ext(r + "/Conv_gate/conv1d/bias");
         for (int ch = 0; ch < F; ++ch) {
@@ -597,6 +627,12 @@ int model_prepack(Model* m, cudaStream_t st) {
     m->up_w[i] = reinterpret_cast<float*>(base + up_w[i]);
     m->up_b[i] = reinterpret_cast<float*>(base + up_b[i]);
   }
+  m->cond_w.assign((size_t)c.n_block * 2, Model::CondAhead());
+  for (const CondOff& co : cond_offs) {
+    Model::CondAhead& ca = m->cond_w[(size_t)co.block * 2 + co.half];
+    ca.w = co.N > 0 ? (void*)(base + co.off) : nullptr;
+    ca.N = co.N; ca.Kpad = co.Kpad; ca.Kc = co.Kc;
+  }
   for (size_t f = 0; f < m->flows.size(); ++f) {
     FlowPack& fp = m->flows[f];
     const FlowOff& fo = offs[f];
@@ -697,6 +733,16 @@ int model_plan(const Model* m, int B, int T, Workspace* w, char* base) {
   w->s = take(M0 * F * as);
   w->u = take(M0 * F * as);
   w->a0 = take((size_t)B * T * 8);  // mixed: rows_i * ceil8(nq_i) * 2 bytes; fp32: rows_i * ceil4(nq_i) * 4 bytes; both <= 8*B*T
+  w->pc[0] = w->pc[1] = nullptr;
+  if (is_mixed(c.precision)) {   // conditioning projections of the first (largest) deep block: rows_i x (flows of the half) x L x 2F, fp32
+    for (int i = 0; i < c.n_block; ++i)
+      if (H * (2 << i) >= AHEAD_MIN_KC) {
+        const size_t elems = ((size_t)B * T >> (i + 1)) * (size_t)((c.n_flow + 1) / 2) * c.n_layer * 2 * F;
+        w->pc[0] = (float*)take(elems * 4);
+        w->pc[1] = (float*)take(elems * 4);
+        break;
+      }
+  }
   w->bytes = off;
   return 0;
 }
@@ -871,10 +917,15 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     g.B = B; g.Ti = Ti;
     for (int k = 0; k < 3; ++k) g.seg[k] = Seg{hin, F, shift_of(k, d), F, k * F};
     g.seg[3] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
-    g.nseg = 4;
+    g.nseg = fp.ahead ? 3 : 4;
     g.W = fp.gate_w[n]; g.ldw = fp.gate_ld; g.N = 2 * F;
     g.e.bias = fp.gate_b[n]; g.e.out0 = w.o; g.e.F = F;
-    prof_begin(m, PROF_GATE, 2.0 * rows * (3 * F + fp.Kc) * 2 * F, st);
+    if (fp.ahead) {   // this layer's slice of the block's conditioning projection (run_cond_ahead)
+      const Model::CondAhead& ca = m->cond_w[(size_t)(&fp - m->flows.data()) / c.n_flow * 2 + fp.cond_half];
+      g.e.in0 = w.pc[fp.cond_half] + (size_t)(fp.ahead_slot + n) * 2 * F;
+      g.e.ld = ca.N;
+    }
+    prof_begin(m, PROF_GATE, 2.0 * rows * (3 * F + (fp.ahead ? 0 : fp.Kc)) * 2 * F, st);
     if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
     prof_end(m, st);
 
@@ -924,16 +975,41 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
 
 // The dependent chain of flows of one pass, on the workspace's X buffer (all pointers inside are workspace / pack pointers,
 // so the captured graph stays valid as long as the workspace and the prepacked weights do).
+// Conditioning projections of a deep block (FlowPack::ahead): P_h[rows, slices * 2F] = c_h . W_c for both mel halves, all flows and
+// layers of the block in one wide GEMM each (modules.py:117-118: _filter_conv_c / _gate_conv_c do not depend on the flow state).
+static int run_cond_ahead(Model* m, const Workspace& w, int block, int B, int Ti, cudaStream_t st) {
+  if (m->cond_w.empty()) return 0;
+  for (int h = 0; h < 2; ++h) {
+    const Model::CondAhead& ca = m->cond_w[(size_t)block * 2 + h];
+    if (!ca.w) continue;
+    FWN_CHECK(w.pc[h], "internal: workspace has no projection buffer");
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    g.seg[0] = Seg{h == 0 ? w.cA : w.cB, ca.Kc, 0, ca.Kc, 0};
+    g.nseg = 1; g.N = ca.N;
+    g.e.out0 = w.pc[h]; g.e.ld = ca.N; g.e.F = m->cfg.filter_size;
+    prof_begin(m, PROF_GATE, 2.0 * B * Ti * ca.Kc * ca.N, st);
+    m->launches++;
+    if (tc_gemm16(g, EPI_PLAIN_F32, ca.w, ca.Kpad, ca.N, m->cfg.precision == FWN_MIXED_FP16, st)) return 1;
+    prof_end(m, st);
+  }
+  return 0;
+}
+
 static int run_chain(Model* m, const Workspace& w, int B, int T, bool reverse, cudaStream_t st) {
   const fwn_config& cf = m->cfg;
   if (!reverse) {
-    for (int i = 0; i < cf.n_block; ++i)
+    for (int i = 0; i < cf.n_block; ++i) {
+      if (run_cond_ahead(m, w, i, B, T >> (i + 1), st)) return 1;
       for (int j = 0; j < cf.n_flow; ++j)
         if (run_flow(m, w, m->flows[(size_t)i * cf.n_flow + j], w.x, B, T >> (i + 1), false, st)) return 1;
+    }
   } else {
-    for (int i = cf.n_block - 1; i >= 0; --i)
+    for (int i = cf.n_block - 1; i >= 0; --i) {
+      if (run_cond_ahead(m, w, i, B, T >> (i + 1), st)) return 1;
       for (int j = cf.n_flow - 1; j >= 0; --j)
         if (run_flow(m, w, m->flows[(size_t)i * cf.n_flow + j], w.x, B, T >> (i + 1), true, st)) return 1;
+    }
   }
   return 0;
 }
@@ -1024,6 +1100,7 @@ int model_forward(Model* m, const float* x, const float* c, const int32_t* g, in
   if (ddi) {
     for (int i = 0; i < cf.n_block; ++i) {
       const int Ti = T >> (i + 1);
+      if (run_cond_ahead(m, w, i, B, Ti, st)) return 1;
       for (int j = 0; j < cf.n_flow; ++j) {
         const FlowPack& fp = m->flows[(size_t)i * cf.n_flow + j];
         if (ddi_flow(m, fp, X, (int64_t)B * Ti, w.ddi, st)) return 1;

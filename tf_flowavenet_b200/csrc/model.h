@@ -20,6 +20,7 @@ struct ParamDesc {
 };
 
 constexpr int MAX_LAYERS = 8;
+constexpr int AHEAD_MIN_KC = 2560;   // blocks whose conditioning half has at least this many channels run their projections ahead
 
 enum GemmId { GEMM_GATE0 = 0, GEMM_RS0 = MAX_LAYERS, GEMM_FINAL = 2 * MAX_LAYERS, GEMM_ZERO = 2 * MAX_LAYERS + 1, GEMM_FRONT = 2 * MAX_LAYERS + 2,
               GEMM_IDS = 2 * MAX_LAYERS + 3 };
@@ -42,6 +43,11 @@ struct FlowPack {
   void* final_w; float* final_b;
   void* zero_w;  float* zero_b;
   int gate_ld, rs_ld[MAX_LAYERS], final_ld, zero_ld;
+  // mixed modes, deep blocks (K_c >= AHEAD_MIN_KC): the conditioning projections c_a . W_c of all flows / layers of the block do not
+  // depend on the flow state, so one wide GEMM per (block, mel half) computes them ahead of the dependent chain (cond_w below) and
+  // the gate GEMMs reduce over the 768 conv inputs only, adding their slice [rows, 2F] of the projection in the epilogue.
+  int ahead;        // 1: this flow's gate GEMMs take the projection from Workspace::pc[cond_half]
+  int ahead_slot;   // first of this flow's n_layer slices (of 2F columns) in the projection
   W3 w3[GEMM_IDS];   // indexed by GemmId; p == nullptr when absent (mixed mode, front conv)
 };
 
@@ -52,6 +58,7 @@ struct Workspace {
   float* up[2];
   void *cA, *cB, *h0, *h1, *o, *s, *u;
   void* a0;       // mixed mode: bf16 [rows, ceil8(nq)] ActNorm'd pass-through half of x (A operand of the front conv)
+  float* pc[2];   // mixed modes: conditioning projections of the current deep block, one per mel half: fp32 [rows_i, slices * 2F]
   size_t bytes;
 };
 
@@ -97,6 +104,9 @@ struct Model {
   float* up_w[4] = {nullptr, nullptr, nullptr, nullptr};
   float* up_b[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_an_logdet = nullptr;
+  // conditioning-ahead operands (mixed modes): per (block, mel half) 16-bit [N = slices * 2F][Kpad], K in the physical order of cA / cB
+  struct CondAhead { void* w = nullptr; int N = 0, Kpad = 0, Kc = 0; };
+  std::vector<CondAhead> cond_w;   // [n_block * 2]; w == nullptr where the block keeps the projection inside its gate GEMMs
   // tcgen05 engine state
   TcPlan* tc = nullptr;
   int plan_B = -1, plan_T = -1;

@@ -28,6 +28,7 @@ void train_free(Model* m) {
   for (auto e : t->set_done) if (e) cudaEventDestroy(e);
   for (auto e : t->cond_ready) cudaEventDestroy(e);
   for (auto& b : t->buckets) if (b.ready) cudaEventDestroy(b.ready);
+  for (auto& g : t->step_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (t->side) cudaStreamDestroy(t->side);
   delete t;
   m->train = nullptr;
@@ -426,7 +427,7 @@ int train_finish_block(Model* m, int block, float* grads, cudaStream_t st) {
   m->launches += 2;
   if (scatter_grad(t->gwall + bk.wall0, t->wmap + bk.wall0, grads, bk.wall1 - bk.wall0, s1)) return 1;
   if (fold_backward(m->raw, grads, t->d_folds, t->d_fwork + bk.work0, bk.work1 - bk.work0, m->raw_floats, s1)) return 1;
-  FWN_CUDA(cudaEventRecord(bk.ready, s1));
+  FWN_CUDA(cudaEventRecordWithFlags(bk.ready, s1, t->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   return 0;
 }
 
@@ -456,7 +457,8 @@ int train_upsampler_backward(Model* m, const float* cmel, const float* up0, floa
       return 1;
   }
   // the upsampler variables (and the speaker embeddings, whose gradient is identically zero: SURVEY F6) close the gradient
-  for (size_t k = (size_t)c.n_block; k < t->buckets.size(); ++k) FWN_CUDA(cudaEventRecord(t->buckets[k].ready, st));
+  for (size_t k = (size_t)c.n_block; k < t->buckets.size(); ++k)
+    FWN_CUDA(cudaEventRecordWithFlags(t->buckets[k].ready, st, t->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   return 0;
 }
 

@@ -72,6 +72,12 @@ struct TrainState {
   // the caller's communication stream, utils.py:34-60) overlaps the backward pass of the blocks still to come.
   struct Bucket { int64_t off, count; int64_t wall0, wall1; int work0, work1; cudaEvent_t ready; };
   std::vector<Bucket> buckets;
+  // 16-bit mode: the whole loss-and-gradients pass (~1 400 launches on two streams) captured once per (shape, buffers) and replayed.
+  // While capturing, the bucket events are recorded as EXTERNAL event nodes so that the caller's communication stream can still wait
+  // on them after every replay.
+  struct StepGraph { int B, T, dual; const void *ws, *grads, *lp, *ld; int state; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<StepGraph> step_graphs;
+  bool capturing = false;
   cudaEvent_t next_event() {
     if (ev.empty()) {
       ev.resize(64);

@@ -31,7 +31,7 @@ struct Tape16 {   // saved activations of one flow (16-bit unless noted)
 };
 struct Ws16 {
   double* sums;
-  float *X, *dX, *up0, *dup0, *cA32, *cB32, *dcA, *dcB;
+  float *X, *dX, *cmel, *up0, *dup0, *cA32, *cB32, *dcA, *dcB;   // cmel: the step's own copy of the mel input (fixed address)
   void *cA, *cB;   // bf16 conditioning planes (GEMM operands)
   struct BwdSet { void* dnet; float* da0; void *du, *ds, *dobuf; void* dfg[MAX_LAYERS]; void* r[MAX_LAYERS]; } set[2];   // alternate per flow
   std::vector<Tape16> tape;
@@ -58,6 +58,7 @@ int plan16(const Model* m, int B, int T, Ws16* w, char* base) {
   w->sums = reinterpret_cast<double*>(take(16 * 8));
   w->X = (float*)take(BT * 4);
   w->dX = (float*)take(BT * 4);
+  w->cmel = (float*)take((size_t)B * (T / m->hop) * c.num_mels * 4);
   const int s_last = c.upsample_scales[c.n_upsample - 1];
   const size_t up_elems = c.n_upsample > 1 ? (size_t)B * (T / s_last) * c.num_mels : 0;
   w->up0 = (float*)take(up_elems * 4);
@@ -287,20 +288,14 @@ int64_t train16_workspace_bytes(const Model* m, int B, int T) {
   return (int64_t)w.bytes;
 }
 
-int train16_loss_and_grads(Model* m, const float* x, const float* cmel, const int32_t* gspk, int B, int T, float* logp_out, float* logdet_out,
-                           float* grads, int64_t grad_floats, void* ws, int64_t ws_bytes, cudaStream_t st) {
+// Everything of the step that depends only on buffers inside the workspace / the handle: capturable.
+static int step_body(Model* m, const Ws16& w, int B, int T, float* logp_out, float* logdet_out, float* grads, cudaStream_t st) {
   const fwn_config& c = m->cfg;
-  FWN_CHECK(c.filter_size == 256 && c.num_mels % 8 == 0, "bf16 training needs filter_size 256 and num_mels %% 8 == 0 (TMA strides / tile shape)");
-  FWN_CHECK(c.n_upsample <= 2, "training supports at most two upsampling stages");
-  Ws16 w;
-  if (plan16(m, B, T, &w, (char*)ws)) return 1;
-  FWN_CHECK(ws && ws_bytes >= (int64_t)w.bytes, "workspace too small: need %lld bytes, got %lld", (long long)w.bytes, (long long)ws_bytes);
   TrainState* t = m->train;
-  m->launches = 0;
   const size_t BT = (size_t)B * T;
   const int H = c.num_mels / 2;
   const bool dual = train_dual_stream();
-  FWN_CUDA(cudaMemcpyAsync(w.X, x, BT * 4, cudaMemcpyDeviceToDevice, st));
+  const float* cmel = w.cmel;
   FWN_CUDA(cudaMemsetAsync(w.sums, 0, 8 * sizeof(double), st));
   FWN_CUDA(cudaMemsetAsync(grads, 0, (size_t)train_grad_floats(m) * 4, st));
   FWN_CUDA(cudaMemsetAsync(t->gwall, 0, (size_t)m->wall_floats * 4, st));
@@ -348,6 +343,79 @@ int train16_loss_and_grads(Model* m, const float* x, const float* cmel, const in
     FWN_CUDA(cudaStreamWaitEvent(st, e, 0));
   }
   return train_upsampler_backward(m, cmel, w.up0, w.dup0, w.cA32, w.cB32, w.dcA, w.dcB, B, T, grads, st);
+}
+
+// FWN_TRAIN_GRAPH=0 launches the step eagerly every time (diagnostics / A-B timing)
+static bool step_graph_enabled() {
+  const char* e = getenv("FWN_TRAIN_GRAPH");
+  return !(e && e[0] == '0');
+}
+
+int train16_loss_and_grads(Model* m, const float* x, const float* cmel, const int32_t* gspk, int B, int T, float* logp_out, float* logdet_out,
+                           float* grads, int64_t grad_floats, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const fwn_config& c = m->cfg;
+  FWN_CHECK(c.filter_size == 256 && c.num_mels % 8 == 0, "bf16 training needs filter_size 256 and num_mels %% 8 == 0 (TMA strides / tile shape)");
+  FWN_CHECK(c.n_upsample <= 2, "training supports at most two upsampling stages");
+  Ws16 w;
+  if (plan16(m, B, T, &w, (char*)ws)) return 1;
+  FWN_CHECK(ws && ws_bytes >= (int64_t)w.bytes, "workspace too small: need %lld bytes, got %lld", (long long)w.bytes, (long long)ws_bytes);
+  TrainState* t = m->train;
+  m->launches = 0;
+  // the caller's inputs go into the workspace first: everything after this touches fixed addresses only
+  FWN_CUDA(cudaMemcpyAsync(w.X, x, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
+  FWN_CUDA(cudaMemcpyAsync(w.cmel, cmel, (size_t)B * (T / m->hop) * c.num_mels * 4, cudaMemcpyDeviceToDevice, st));
+  const int dual = train_dual_stream() ? 1 : 0;
+  TrainState::StepGraph* g = nullptr;
+  if (step_graph_enabled()) {
+    for (auto& e : t->step_graphs)
+      if (e.B == B && e.T == T && e.dual == dual && e.ws == ws && e.grads == grads && e.lp == logp_out && e.ld == logdet_out) g = &e;
+    if (!g) {   // first step with these buffers: eager (kernel attributes, tensor-map cache); the next one is captured
+      if (t->step_graphs.size() >= 8) {
+        for (auto& e : t->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+        t->step_graphs.clear();
+      }
+      t->step_graphs.push_back(TrainState::StepGraph{B, T, dual, ws, grads, logp_out, logdet_out, 0, nullptr, 0});
+      return step_body(m, w, B, T, logp_out, logdet_out, grads, st);
+    }
+    if (g->state == 0) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();   // e.g. the legacy default stream: stay eager on this stream
+        g->state = -1;
+        return step_body(m, w, B, T, logp_out, logdet_out, grads, st);
+      }
+      t->capturing = true;
+      const int64_t before = m->launches;
+      const int rc = step_body(m, w, B, T, logp_out, logdet_out, grads, st);
+      t->capturing = false;
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        g->state = -1;
+        if (rc) return 1;
+        m->launches = before;
+        return step_body(m, w, B, T, logp_out, logdet_out, grads, st);
+      }
+      g->launches = m->launches - before;
+      m->launches = before;
+      e = cudaGraphInstantiate(&g->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        g->exec = nullptr;
+        g->state = -1;
+        return step_body(m, w, B, T, logp_out, logdet_out, grads, st);
+      }
+      g->state = 1;
+    }
+    if (g->state == 1) {
+      FWN_CUDA(cudaGraphLaunch(g->exec, st));
+      m->launches += g->launches;
+      return 0;
+    }
+  }
+  return step_body(m, w, B, T, logp_out, logdet_out, grads, st);
 }
 
 }  // namespace fwn

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Staged GPU check with tight per-stage timeouts: a hung kernel costs one stage's timeout, not the whole budget.
+# usage (on the GPU box): bash tools/gpu_check.sh [stage ...]   stages: mixed train16 dbg16 baseline train model bench
+mkdir -p gpurun_out
+run() {  # name timeout cmd...
+  local name=$1 t=$2; shift 2
+  timeout "$t" "$@" > gpurun_out/chk_$name.log 2>&1
+  local rc=$?
+  echo "== $name rc=$rc"
+  grep -E "^\.?(bf16|loss|wgrad|C2|C3|deep|C4|mixed|step|    Block|    conv)|passed|failed|Error|error" gpurun_out/chk_$name.log | tail -${TAILN:-25} | cut -c1-330
+  if [ $rc -eq 124 ]; then echo "!! $name TIMED OUT -- stopping"; exit 0; fi
+}
+for s in "$@"; do
+  case $s in
+    mixed) run mixed 240 python -m pytest tests/test_gpu_mixed.py -m gpu -q -s -x ;;
+    dbg16) FWN_TRACE=1 FWN_SYNC_DEBUG=1 run dbg16 100 python tools/debug_train16.py 8 8 25; tail -2 gpurun_out/chk_dbg16.log | cut -c1-300 ;;
+    train16) run train16 400 python -m pytest tests/test_gpu_train_bf16.py -m gpu -q -s ;;
+    baseline) run baseline 500 python -m pytest tests/test_gpu_baseline_shapes.py -m gpu -q -s ;;
+    train) run train 500 python -m pytest tests/test_gpu_train.py -m gpu -q -s ;;
+    model) run model 400 python -m pytest tests/test_gpu_model.py tests/test_gpu_ops.py -m gpu -q -s ;;
+    *) echo "unknown stage $s" ;;
+  esac
+done
