@@ -13,7 +13,7 @@ run() {  # name timeout cmd...
 for s in "$@"; do
   case $s in
     mixed) run mixed 240 python -m pytest tests/test_gpu_mixed.py -m gpu -q -s -x ;;
-    dbg16) FWN_TRACE=1 FWN_SYNC_DEBUG=1 run dbg16 100 python tools/debug_train16.py 8 8 25; tail -2 gpurun_out/chk_dbg16.log | cut -c1-300 ;;
+    dbg16) FWN_TRAIN_GRAPH=0 FWN_TRACE=1 FWN_SYNC_DEBUG=1 run dbg16 100 python tools/debug_train16.py 8 8 25; tail -2 gpurun_out/chk_dbg16.log | cut -c1-300 ;;
     train16) run train16 400 python -m pytest tests/test_gpu_train_bf16.py -m gpu -q -s ;;
     baseline) run baseline 500 python -m pytest tests/test_gpu_baseline_shapes.py -m gpu -q -s ;;
     train) run train 500 python -m pytest tests/test_gpu_train.py -m gpu -q -s ;;
