@@ -28,6 +28,7 @@ struct Tape16 {   // saved activations of one flow (16-bit unless noted)
   void *h[MAX_LAYERS], *o[MAX_LAYERS], *sg[MAX_LAYERS];   // layer input, gated output, sigmoid(g)   [rows, F]
   void *s, *u;    // relu(sum of skips), relu(final conv)                                            [rows, F]
   float* net;     // fp32 (log_s, t) [rows, ceil4(2 nq)]
+  float* pc[MAX_LAYERS];   // deep blocks: fp32 [rows, 2F] conditioning projection of each layer, computed ahead on the side stream
 };
 struct Ws16 {
   double* sums;
@@ -83,6 +84,7 @@ int plan16(const Model* m, int B, int T, Ws16* w, char* base) {
       for (int n = 0; n < L; ++n) { tp.h[n] = take(M * F * 2); tp.o[n] = take(M * F * 2); tp.sg[n] = take(M * F * 2); }
       tp.s = take(M * F * 2); tp.u = take(M * F * 2);
       tp.net = (float*)take(M * ceil4(2 * nq) * 4);
+      for (int n = 0; n < L; ++n) tp.pc[n] = H * (2 << i) >= AHEAD_MIN_KC ? (float*)take(M * 2 * F * 4) : nullptr;
     }
   }
   w->bytes = off;
@@ -118,8 +120,9 @@ int flow_forward16(Model* m, const Ws16& w, const FlowPack& fp, const Tape16& tp
     g.B = B; g.Ti = Ti;
     for (int k = 0; k < 3; ++k) g.seg[k] = Seg{tp.h[n], F, shift_of(c, k, d), F, k * F};
     g.seg[3] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
-    g.nseg = 4; g.N = 2 * F;
+    g.nseg = tp.pc[n] ? 3 : 4; g.N = 2 * F;
     g.e.bias = fp.gate_b[n]; g.e.out0 = tp.o[n]; g.e.tape = tp.sg[n]; g.e.F = F;
+    if (tp.pc[n]) { g.e.in0 = tp.pc[n]; g.e.ld = 2 * F; }   // the projection was computed ahead (cond_forward16)
     if (gemm16(m, g, EPI_GATE, fp.w3[GEMM_GATE0 + n], st)) return 1;
     const bool last = n == L - 1;
     GemmArgs r = {};
@@ -152,6 +155,24 @@ int flow_forward16(Model* m, const Ws16& w, const FlowPack& fp, const Tape16& tp
     g.e.b_odd = fp.b_odd;
     g.e.out1 = tp.net; g.e.ld = ceil4(2 * nq);
     if (gemm16(m, g, EPI_AFFINE, fp.w3[GEMM_ZERO], st)) return 1;
+  }
+  return 0;
+}
+
+// Deep blocks (K_c >= AHEAD_MIN_KC: thousands of conditioning channels against a few hundred rows): the projections c_a . W_c do not
+// depend on the flow state, so they run ahead of the dependent chain -- on the side stream, over a flat row axis -- into fp32
+// buffers the gate GEMMs add in their epilogue; the chain's gate GEMMs then reduce over the 768 conv inputs only.
+int cond_forward16(Model* m, const Ws16& w, const FlowPack& fp, const Tape16& tp, int B, int Ti, cudaStream_t st) {
+  const int F = m->cfg.filter_size, L = m->cfg.n_layer;
+  const void* cond = fp.cond_half == 0 ? w.cA : w.cB;
+  for (int n = 0; n < L; ++n) {
+    if (!tp.pc[n]) continue;
+    GemmArgs g = {};
+    g.B = B; g.Ti = Ti;
+    g.seg[0] = Seg{cond, fp.Kc, 0, fp.Kc, 3 * F};
+    g.nseg = 1; g.N = 2 * F;
+    g.e.out0 = tp.pc[n]; g.e.ld = 2 * F; g.e.F = F;
+    if (gemm16(m, g, EPI_PLAIN_F32, fp.w3[GEMM_GATE0 + n], st)) return 1;
   }
   return 0;
 }
@@ -313,11 +334,29 @@ static int step_body(Model* m, const Ws16& w, int B, int T, float* logp_out, flo
     if (upsample_stage(last == 0 ? cmel : w.up0, m->up_w[last], m->up_b[last], w.cA, w.cB, B, Tm, c.num_mels, c.upsample_scales[last], true, 1, st))
       return 1;
   }
-  for (int i = 0; i < c.n_block; ++i)
+  {
+    cudaStream_t s1 = dual ? t->side : st;
+    if (dual) {   // the side stream sees the upsampled conditioning
+      cudaEvent_t e = t->next_event();
+      FWN_CUDA(cudaEventRecord(e, st));
+      FWN_CUDA(cudaStreamWaitEvent(s1, e, 0));
+    }
+    for (int i = 0; i < c.n_block; ++i) {   // conditioning projections of the deep blocks, ahead of the chain
+      if (!w.tape[(size_t)i * c.n_flow].pc[0]) continue;
+      for (int j = 0; j < c.n_flow; ++j) {
+        const size_t f = (size_t)i * c.n_flow + j;
+        if (cond_forward16(m, w, m->flows[f], w.tape[f], B, T >> (i + 1), s1)) return 1;
+      }
+      if (dual) FWN_CUDA(cudaEventRecord(t->cond_ready[i], s1));
+    }
+  }
+  for (int i = 0; i < c.n_block; ++i) {
+    if (dual && w.tape[(size_t)i * c.n_flow].pc[0]) FWN_CUDA(cudaStreamWaitEvent(st, t->cond_ready[i], 0));
     for (int j = 0; j < c.n_flow; ++j) {
       const size_t f = (size_t)i * c.n_flow + j;
       if (flow_forward16(m, w, m->flows[f], w.tape[f], B, T >> (i + 1), st)) return 1;
     }
+  }
   if (sumsq(w.X, w.sums + 1, (int64_t)BT, st)) return 1;
   if (finish_forward(w.sums, m->d_an_logdet, logp_out, logdet_out, (double)BT, st)) return 1;
   // ---- backward

@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       }
       const int lg = warp & 3;                      // TMEM lane group this warp may read
       float* tile = reinterpret_cast<float*>(stage_base);
-      mbar_wait(tmem_full, 0);                      // every MMA has completed: the staging area is free as well
+      mbar_wait(tmem_full, 0);                      // every MMA has completed: the staging area is free for the tensor pipe ...
       tcgen05_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // ... and every epilogue warp has finished its bias sums over the last stages
       const int r = lg * 32 + lane;
 #pragma unroll 1
       for (int cc = 0; cc < BNW; cc += 32) {

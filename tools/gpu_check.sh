@@ -18,6 +18,18 @@ for s in "$@"; do
     baseline) run baseline 500 python -m pytest tests/test_gpu_baseline_shapes.py -m gpu -q -s ;;
     train) run train 500 python -m pytest tests/test_gpu_train.py -m gpu -q -s ;;
     model) run model 400 python -m pytest tests/test_gpu_model.py tests/test_gpu_ops.py -m gpu -q -s ;;
+    bench_*) w=${s#bench_}; timeout 300 python bench.py --workload ${w%%,*} --steps 10 --warmup 3 --no-cpu-baseline $BENCH_ARGS > gpurun_out/chk_$s.json 2> gpurun_out/chk_$s.err
+             echo "== $s rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/chk_$s.json")); r = d["roofline"]
+    print("   ms/step %.3f  value %.4g  frac %.3f  launches %s  e2e %.4g" % (d["ms_per_step"], d["value"], r["frac"], d.get("gpu_launches"), d["e2e"]["value"]))
+    if "phases_ms_per_step" in r: print("   phases", r["phases_ms_per_step"])
+    if "families" in r: print("   " + "  ".join("%s %.2f ms" % (k, v["ms"] / d["steps"]) for k, v in r["families"].items()))
+except Exception as e:
+    print("   ERR", e); print(open("gpurun_out/chk_$s.err").read()[-600:])
+PY
+             ;;
     *) echo "unknown stage $s" ;;
   esac
 done
