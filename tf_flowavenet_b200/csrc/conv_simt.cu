@@ -287,6 +287,80 @@ int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st) {
   return 0;
 }
 
+// Front conv of the shallow blocks (nq = C_x/2 <= 4 input channels: 6 .. 24 MAC per output) for the mixed modes, straight from the
+// flow variable: h0[row, ch] = relu(b[ch] + sum_{k,q} a(row + shift_k, q) W[k,q,ch]) with a = ActNorm'd pass-through half of x (fp32,
+// zero outside the utterance = tf.pad, modules.py:27).  One warp per output row, one lane per 8 channels: the lane keeps its
+// 3 nq x 8 weights in registers, the 3 nq inputs of a row are warp-uniform (broadcast) loads, and a row leaves as 32 contiguous
+// 16-byte stores.  Write-bound (512 B per row); replaces front_pack + a K = 3 x 16 tensor-core GEMM whose operand tiles are 94 % padding.
+template <int NQ, typename T16>
+__global__ void __launch_bounds__(256) front_direct_kernel(const FrontArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ch0 = lane * 8;
+  float w[3 * NQ][8], bias[8];
+#pragma unroll
+  for (int kq = 0; kq < 3 * NQ; ++kq) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)kq * a.F + ch0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)kq * a.F + ch0 + 4));
+    w[kq][0] = w0.x; w[kq][1] = w0.y; w[kq][2] = w0.z; w[kq][3] = w0.w;
+    w[kq][4] = w1.x; w[kq][5] = w1.y; w[kq][6] = w1.z; w[kq][7] = w1.w;
+  }
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + 4));
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
+  int off[NQ];          // physical offset of logical pass-through channel q inside a row of X
+  float ab[NQ], as[NQ]; // ActNorm on load (identity in the reverse direction)
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) { off[q] = 0; ab[q] = 0.f; as[q] = 1.f; }
+  for (int o = 0; o < a.Cx; ++o) {
+    const int l = __ldg(a.off2log + o);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      if (l == q) {
+        off[q] = o;
+        if (a.an_b) { ab[q] = __ldg(a.an_b + o); as[q] = __ldg(a.an_s + o); }
+      }
+  }
+  const int Ti = a.Ti, Cx = a.Cx;
+  const int64_t rows = (int64_t)a.B * Ti;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    const int t = (int)(row % Ti);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int tt = t + a.shift[k];
+      if (tt < 0 || tt >= Ti) continue;   // zero padding at the utterance edges
+      const float* xr = a.X + (row + a.shift[k]) * Cx;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float v = (__ldg(xr + off[q]) + ab[q]) * as[q];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, w[k * NQ + q][j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    *reinterpret_cast<uint4*>(reinterpret_cast<T16*>(a.H) + row * a.F + ch0) =
+        make_uint4(pack2<T16>(acc[0], acc[1]), pack2<T16>(acc[2], acc[3]), pack2<T16>(acc[4], acc[5]), pack2<T16>(acc[6], acc[7]));
+  }
+}
+bool front_direct_supported(const FrontArgs& a) { return a.F == 256 && (a.nq == 1 || a.nq == 2 || a.nq == 4); }
+int front_direct(const FrontArgs& a, bool fp16, cudaStream_t st) {
+  if (a.B <= 0 || a.Ti <= 0) return 0;
+  FWN_CHECK(front_direct_supported(a), "front_direct: needs F = 256 and nq in {1, 2, 4}");
+  const int64_t rows = (int64_t)a.B * a.Ti;
+  const int grid = (int)std::min<int64_t>(cdiv(rows, 8), (int64_t)num_sms() * 8);
+#define FWN_FD(NQ)                                                                   \
+  if (fp16) front_direct_kernel<NQ, __half><<<grid, 256, 0, st>>>(a);                \
+  else front_direct_kernel<NQ, __nv_bfloat16><<<grid, 256, 0, st>>>(a)
+  if (a.nq == 1) { FWN_FD(1); } else if (a.nq == 2) { FWN_FD(2); } else { FWN_FD(4); }
+#undef FWN_FD
+  FWN_LAUNCH_CHECK();
+  return 0;
+}
+
 // Gather the pass-through half of the flow variable, apply ActNorm (forward direction) and cast to bf16: the A operand of the
 // tensor-core front conv.  One thread per (row, 8 output columns): X rows are contiguous so a warp reads whole rows.
 template <typename T16>

@@ -511,6 +511,63 @@ __global__ void upsample_warp_kernel(const float* __restrict__ in, const float* 
     }
   }
 }
+// Chunk-per-thread upsampler (mels % 8 == 0, and (mels/2) % 8 == 0 when SPLIT): one thread = 8 consecutive mel bins of one output
+// time step = one 16-byte (16-bit) or 32-byte (fp32) store; consecutive threads write consecutive chunks of a plane, so every warp
+// store instruction covers 512 contiguous bytes.  The 2 x 10 inputs a thread needs come from the (tiny, L1-resident) stage input:
+// an input frame is re-used by the s output steps it feeds.  No shared-memory staging, no warp synchronisation: the kernel runs at
+// the write bandwidth of its output.
+template <typename TOut, bool SPLIT>
+__global__ void __launch_bounds__(256) upsample_chunk_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias_p,
+                                                             TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
+  extern __shared__ float sw[];  // [2s*3]
+  for (int i = threadIdx.x; i < 2 * s * 3; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int To = Tm * s, half = mels / 2;
+  const int pm = SPLIT ? half : mels;            // mel bins per output row of one plane
+  const int gpr = pm / 8;                        // 8-mel chunks per row
+  const int64_t rows = (int64_t)B * To;
+  const int64_t per_plane = rows * gpr;
+  const int64_t total = per_plane * (SPLIT ? 2 : 1);
+  const float bias = __ldg(bias_p);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int pl = SPLIT ? (int)(idx / per_plane) : 0;
+    const int64_t rem = idx - (int64_t)pl * per_plane;
+    const int64_t bt = rem / gpr;
+    const int gi = (int)(rem - bt * gpr);
+    const int b = (int)(bt / To), i = (int)(bt - (int64_t)b * To);
+    const int q = i + s / 2, r = q % s, j0 = q / s;                 // taps kh = r (frame j0) and r + s (frame j0 - 1)
+    const int m0 = pl * half + gi * 8;                             // first mel bin of the chunk
+    float x1[10], x0[10];                                          // frames j0 / j0-1, mel bins m0-1 .. m0+8 (zero outside)
+    const float* f1 = in + ((int64_t)b * Tm + j0) * mels;
+    const float* f0 = f1 - mels;
+    const bool v1 = j0 < Tm, v0 = j0 >= 1;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const int mm = m0 - 1 + k;
+      const bool ok = mm >= 0 && mm < mels;
+      x1[k] = (ok && v1) ? __ldg(f1 + mm) : 0.f;
+      x0[k] = (ok && v0) ? __ldg(f0 + mm) : 0.f;
+    }
+    const float a0 = sw[r * 3], a1 = sw[r * 3 + 1], a2 = sw[r * 3 + 2];
+    const float c0 = sw[(r + s) * 3], c1 = sw[(r + s) * 3 + 1], c2 = sw[(r + s) * 3 + 2];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // out[m] = sum_kw in[m + 1 - kw] * w[kh][kw]
+      float v = bias;
+      v = fmaf(x1[j + 2], a0, fmaf(x1[j + 1], a1, fmaf(x1[j], a2, v)));
+      v = fmaf(x0[j + 2], c0, fmaf(x0[j + 1], c1, fmaf(x0[j], c2, v)));
+      acc[j] = fmaxf(v, 0.4f * v);
+    }
+    TOut* dst = (SPLIT && pl == 1 ? out1 : out0) + bt * pm + gi * 8;
+    if constexpr (sizeof(TOut) == 2) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<TOut>(acc[0], acc[1]), pack2<TOut>(acc[2], acc[3]),
+                                                  pack2<TOut>(acc[4], acc[5]), pack2<TOut>(acc[6], acc[7]));
+    } else {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
 // weight norm of the [2s,3,1,1] kernel over axes [0,2] => per kw column (convolutional.py:186)
 __global__ void upsample_wn_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int s) {
   int kw = threadIdx.x;
@@ -532,7 +589,17 @@ int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* o
   if (n == 0) return 0;
   int grid = ew_grid(n, 256);
   size_t smem = 2 * (size_t)s * 3 * sizeof(float);
-  if (mels % 16 == 0 && (reinterpret_cast<uintptr_t>(out0) % 16) == 0 && (!split || reinterpret_cast<uintptr_t>(out1) % 16 == 0)) {
+  const bool al16 = (reinterpret_cast<uintptr_t>(out0) % 16) == 0 && (!split || reinterpret_cast<uintptr_t>(out1) % 16 == 0);
+  static const bool use_warp_kernel = getenv("FWN_UPSAMPLE_WARP") != nullptr;   // the round-1 kernel, kept for A/B timing
+  if (!use_warp_kernel && al16 && mels % 8 == 0 && (!split || (mels / 2) % 8 == 0)) {
+    const int64_t chunks = n / 8;
+    const int g2 = (int)std::min<int64_t>(cdiv(chunks, 256), (int64_t)num_sms() * 32);
+    if (split) upsample_chunk_kernel<TOut, true><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    else upsample_chunk_kernel<TOut, false><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    FWN_LAUNCH_CHECK();
+    return 0;
+  }
+  if (mels % 16 == 0 && al16) {
     const int wpb = 8;
     const size_t sm2 = smem + (size_t)wpb * 2 * (mels + 2) * sizeof(float);
     const int64_t ntask = (int64_t)B * (Tm + 1);

@@ -688,12 +688,14 @@ int make_w_map(CUtensorMap* map, const void* base, int Npad, int Kpad, int bn) {
   return 0;
 }
 
-// FWN_WS_MULTICAST=0 runs the weight-stationary GEMMs without cluster multicast of the activation chunks (diagnostics / A-B timing)
+// FWN_WS_MULTICAST=1 runs the weight-stationary GEMMs as clusters that receive their activation chunks by TMA multicast.  Measured
+// on C3 (profiles/r2_ws_multicast.md): res|skip 12.7 -> 15.0 ms per pass, final conv 3.1 -> 3.2 ms -- the lock-step of the cluster
+// (a stage is re-armed only after every CTA of the cluster released it) costs more than the L2->SM traffic it saves.  Off by default.
 static bool ws_multicast() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FWN_WS_MULTICAST");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }

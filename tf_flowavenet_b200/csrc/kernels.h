@@ -115,6 +115,9 @@ struct FrontArgs {
   int shift[3];
 };
 int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st);
+// mixed modes, nq <= 4: the same conv straight from X on the CUDA cores, 16-bit output (write-bound; no operand packing)
+bool front_direct_supported(const FrontArgs& a);
+int front_direct(const FrontArgs& a, bool fp16, cudaStream_t st);
 // mixed mode: gather + ActNorm + bf16 cast of the pass-through half: A0[row, q] = a(row, q), q < nq, row pitch kq (zero padded)
 int front_pack(const float* X, int Cx, int nq, int kq, const int* off2log, const float* an_b, const float* an_s, void* A0, int64_t rows,
                bool fp16, cudaStream_t st);

@@ -848,6 +848,15 @@ int run_upsample(const Model* m, const Workspace& w, const float* c_in, int B, i
   return 0;
 }
 
+// FWN_FRONT_DIRECT=0 keeps the shallow blocks' front conv on the tensor-core path (diagnostics / A-B timing)
+static bool front_direct_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_FRONT_DIRECT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static bool fp32_front_on_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -893,6 +902,10 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   } else if (!bf16) {
     m->launches++;
     if (front_conv(fa, false, st)) return 1;
+  } else if (front_direct_supported(fa) && front_direct_enabled()) {
+    // mixed modes, shallow blocks: 6 .. 24 MAC per output straight from X on the CUDA cores (write-bound)
+    m->launches++;
+    if (front_direct(fa, c.precision == FWN_MIXED_FP16, st)) return 1;
   } else {
     // mixed mode: tiny gather/cast kernel, then the front conv is three time-shifted K segments on the tcgen05 engine
     const int kq = (fp.nq + 7) / 8 * 8;
