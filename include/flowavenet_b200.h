@@ -139,6 +139,10 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
  * 3 terms (a1w1 + a1w2 + a2w1) keep ~2^-16..2^-18 per product at half the tensor work (default for the training step; gradients
  * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
+/* Mixed-precision passes: how a ResBlock layer (modules.py:113-128) is launched.  1 = one fused kernel per layer (gate GEMM ->
+ * tanh*sigmoid -> res|skip 1x1 with the gated tile kept in shared memory), 0 = two launches with the gated activations round-tripping
+ * through HBM, -1 = default (fused; environment FWN_FUSE_LAYER=0 disables).  Both give bit-identical results. */
+int fwn_set_layer_fusion(fwn_handle h, int mode);
 /* Compute precision of the training step (the model keeps fp32 master variables either way, utils.py:3-31):
  *   FWN_FP32        fp32-accurate GEMMs (3-way bf16 split on the tensor cores) -- the parity mode (default)
  *   FWN_MIXED_BF16  bf16 operands and tape, fp32 accumulation / reductions / gradients: BASELINE config 5 ("bf16").  bf16 keeps

@@ -52,6 +52,7 @@ SIGNATURES = {
     "fwn_apply_gradients": (_i, [_p, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _l, _p]),
     "fwn_set_split_terms": (_i, [_p, _i, _i]),
     "fwn_set_train_compute": (_i, [_p, _i]),
+    "fwn_set_layer_fusion": (_i, [_p, _i]),
     "fwn_wgrad_bf16": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _p]),
     "fwn_set_train_exact_forward": (_i, [_p, _i]),
     "fwn_get_train_state": (_i, [_p, _i, _fp, _l, _p]),

@@ -209,6 +209,13 @@ int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms) {
   model_drop_graphs(h->m);   // captured launches carry the old setting
   return 0;
 }
+int fwn_set_layer_fusion(fwn_handle h, int mode) {
+  FWN_CHECK(h, "null handle");
+  FWN_CHECK(mode >= -1 && mode <= 1, "layer fusion mode must be -1 (default), 0 or 1");
+  h->m->fuse_layer = mode;
+  model_drop_graphs(h->m);   // captured launches carry the old setting
+  return 0;
+}
 int fwn_set_train_compute(fwn_handle h, int precision) {
   FWN_CHECK(h, "null handle");
   FWN_CHECK(precision == FWN_FP32 || precision == FWN_MIXED_BF16, "training compute precision must be FWN_FP32 or FWN_MIXED_BF16");

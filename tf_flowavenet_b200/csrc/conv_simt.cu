@@ -289,11 +289,19 @@ int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st) {
 
 // Front conv of the shallow blocks (nq = C_x/2 <= 4 input channels: 6 .. 24 MAC per output) for the mixed modes, straight from the
 // flow variable: h0[row, ch] = relu(b[ch] + sum_{k,q} a(row + shift_k, q) W[k,q,ch]) with a = ActNorm'd pass-through half of x (fp32,
-// zero outside the utterance = tf.pad, modules.py:27).  One warp per output row, one lane per 8 channels: the lane keeps its
-// 3 nq x 8 weights in registers, the 3 nq inputs of a row are warp-uniform (broadcast) loads, and a row leaves as 32 contiguous
-// 16-byte stores.  Write-bound (512 B per row); replaces front_pack + a K = 3 x 16 tensor-core GEMM whose operand tiles are 94 % padding.
+// zero outside the utterance = tf.pad, modules.py:27).  Write-bound (512 B per row); replaces front_pack + a K = 3 x 16 tensor-core
+// GEMM whose operand tiles are 94 % padding.  A block walks tiles of FD_ROWS consecutive rows of one utterance: the tile's inputs
+// (+ halo) are gathered once into shared memory -- the NEXT tile's inputs are already in flight in registers while this tile is
+// computed --, then each warp produces 8 rows: a lane owns 8 channels (its 3 nq x 8 weights live in registers), the 3 nq inputs of
+// a row are broadcast shared-memory reads, and a row leaves as 32 contiguous 16-byte stores, 8 independent rows in flight per warp.
+constexpr int FD_ROWS = 64;
 template <int NQ, typename T16>
-__global__ void __launch_bounds__(256) front_direct_kernel(const FrontArgs a) {
+__global__ void __launch_bounds__(256, 2) front_direct_kernel(const FrontArgs a, int lo, int hi, int tiles_per_utt, int n_tiles) {
+  constexpr int SPAN = FD_ROWS + 64;   // rows [t0 + lo, t0 + FD_ROWS + hi) with -32 <= lo <= 0 <= hi <= 32
+  constexpr int PER = (SPAN * NQ + 255) / 256;
+  __shared__ float xs[SPAN * NQ];
+  __shared__ int s_off[NQ];
+  __shared__ float s_ab[NQ], s_as[NQ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch0 = lane * 8;
   float w[3 * NQ][8], bias[8];
@@ -308,53 +316,79 @@ __global__ void __launch_bounds__(256) front_direct_kernel(const FrontArgs a) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + 4));
     bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
   }
-  int off[NQ];          // physical offset of logical pass-through channel q inside a row of X
-  float ab[NQ], as[NQ]; // ActNorm on load (identity in the reverse direction)
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) { off[q] = 0; ab[q] = 0.f; as[q] = 1.f; }
-  for (int o = 0; o < a.Cx; ++o) {
-    const int l = __ldg(a.off2log + o);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-      if (l == q) {
-        off[q] = o;
-        if (a.an_b) { ab[q] = __ldg(a.an_b + o); as[q] = __ldg(a.an_s + o); }
-      }
-  }
-  const int Ti = a.Ti, Cx = a.Cx;
-  const int64_t rows = (int64_t)a.B * Ti;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
-    const int t = (int)(row % Ti);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[j];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int tt = t + a.shift[k];
-      if (tt < 0 || tt >= Ti) continue;   // zero padding at the utterance edges
-      const float* xr = a.X + (row + a.shift[k]) * Cx;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const float v = (__ldg(xr + off[q]) + ab[q]) * as[q];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, w[k * NQ + q][j], acc[j]);
-      }
+  // physical offset of logical pass-through channel q inside a row of X, and its ActNorm (identity in the reverse direction)
+  if (threadIdx.x < a.Cx) {
+    const int o = threadIdx.x, l = __ldg(a.off2log + o);
+    if (l < NQ) {
+      s_off[l] = o;
+      s_ab[l] = a.an_b ? __ldg(a.an_b + o) : 0.f;
+      s_as[l] = a.an_b ? __ldg(a.an_s + o) : 1.f;
     }
+  }
+  __syncthreads();
+  const int Ti = a.Ti, Cx = a.Cx, span = FD_ROWS + hi - lo;
+  // element i of a tile's input window: row t0 + lo + i / NQ, channel i % NQ; 0 outside the utterance
+  auto fetch = [&](int tile, float* v) {
+    const int ub = tile / tiles_per_utt, t0 = (tile - ub * tiles_per_utt) * FD_ROWS;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-    *reinterpret_cast<uint4*>(reinterpret_cast<T16*>(a.H) + row * a.F + ch0) =
-        make_uint4(pack2<T16>(acc[0], acc[1]), pack2<T16>(acc[2], acc[3]), pack2<T16>(acc[4], acc[5]), pack2<T16>(acc[6], acc[7]));
+    for (int p = 0; p < PER; ++p) {
+      const int i = threadIdx.x + p * 256, r = i / NQ, q = i - r * NQ, t = t0 + lo + r;
+      v[p] = 0.f;
+      if (tile < n_tiles && r < span && t >= 0 && t < Ti) v[p] = (__ldg(a.X + ((int64_t)ub * Ti + t) * Cx + s_off[q]) + s_ab[q]) * s_as[q];
+    }
+  };
+  float nxt[PER];
+  int tile = blockIdx.x;
+  fetch(tile, nxt);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();   // every warp is done with the previous tile's window
+#pragma unroll
+    for (int p = 0; p < PER; ++p)
+      if (threadIdx.x + p * 256 < SPAN * NQ) xs[threadIdx.x + p * 256] = nxt[p];
+    __syncthreads();
+    fetch(tile + gridDim.x, nxt);
+    const int ub = tile / tiles_per_utt, t0 = (tile - ub * tiles_per_utt) * FD_ROWS;
+#pragma unroll
+    for (int j8 = 0; j8 < FD_ROWS / 8; ++j8) {
+      const int r = warp + 8 * j8, t = t0 + r;
+      if (t >= Ti) break;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float* xr = xs + (r + a.shift[k] - lo) * NQ;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float v = xr[q];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, w[k * NQ + q][j], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      *reinterpret_cast<uint4*>(reinterpret_cast<T16*>(a.H) + ((int64_t)ub * Ti + t) * a.F + ch0) =
+          make_uint4(pack2<T16>(acc[0], acc[1]), pack2<T16>(acc[2], acc[3]), pack2<T16>(acc[4], acc[5]), pack2<T16>(acc[6], acc[7]));
+    }
   }
 }
-bool front_direct_supported(const FrontArgs& a) { return a.F == 256 && (a.nq == 1 || a.nq == 2 || a.nq == 4); }
+bool front_direct_supported(const FrontArgs& a) {
+  if (!(a.F == 256 && (a.nq == 1 || a.nq == 2 || a.nq == 4) && a.Cx <= 256)) return false;
+  for (int k = 0; k < 3; ++k)
+    if (a.shift[k] < -32 || a.shift[k] > 32) return false;
+  return true;
+}
 int front_direct(const FrontArgs& a, bool fp16, cudaStream_t st) {
   if (a.B <= 0 || a.Ti <= 0) return 0;
-  FWN_CHECK(front_direct_supported(a), "front_direct: needs F = 256 and nq in {1, 2, 4}");
-  const int64_t rows = (int64_t)a.B * a.Ti;
-  const int grid = (int)std::min<int64_t>(cdiv(rows, 8), (int64_t)num_sms() * 8);
-#define FWN_FD(NQ)                                                                   \
-  if (fp16) front_direct_kernel<NQ, __half><<<grid, 256, 0, st>>>(a);                \
-  else front_direct_kernel<NQ, __nv_bfloat16><<<grid, 256, 0, st>>>(a)
+  FWN_CHECK(front_direct_supported(a), "front_direct: needs F = 256, nq in {1, 2, 4} and |shift| <= 32");
+  int lo = 0, hi = 0;
+  for (int k = 0; k < 3; ++k) { lo = std::min(lo, a.shift[k]); hi = std::max(hi, a.shift[k]); }
+  const int tiles_per_utt = (a.Ti + FD_ROWS - 1) / FD_ROWS;
+  const int n_tiles = a.B * tiles_per_utt;
+  const int grid = std::min(n_tiles, num_sms() * 2);
+#define FWN_FD(NQ)                                                                                                   \
+  if (fp16) front_direct_kernel<NQ, __half><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);                \
+  else front_direct_kernel<NQ, __nv_bfloat16><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles)
   if (a.nq == 1) { FWN_FD(1); } else if (a.nq == 2) { FWN_FD(2); } else { FWN_FD(4); }
 #undef FWN_FD
   FWN_LAUNCH_CHECK();

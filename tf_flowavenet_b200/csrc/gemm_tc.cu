@@ -23,6 +23,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "layer_tc.cuh"
 #include "model.h"
 #include "tc_ptx.cuh"
 
@@ -966,6 +967,68 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   a.multicast = (kind == EPI_GATE && gate_multicast()) ? 1 : 0;
   a.fp16 = m->cfg.precision == FWN_MIXED_FP16 ? 1 : 0;
   return tc::tc_launch(a, kind, bn, ws, st);
+}
+
+// Fused ResBlock layer (layer_tc.cu): the gate GEMM `g` and the res|skip 1x1 `r` of one layer in one launch; o never leaves the SM.
+// Supported: the CTA-pair gate path, F = 256, and a 1x1 whose staged epilogue input is single (first layer: h_in; last layer: the
+// running skip sum) -- a middle layer of a deeper WaveNet (residual AND running skip) takes the two-launch path.
+bool tc_layer_supported(const Model* m, const GemmArgs& g, const GemmArgs& r) {
+  if (!m->tc || !gate_multicast() || m->cfg.filter_size != 256) return false;
+  if (g.e.tape || g.e.out1) return false;
+  if (r.e.has_res && r.e.in1) return false;
+  return true;
+}
+int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st) {
+  TcPlan* p = m->tc;
+  FWN_CHECK(p, "tcgen05 engine not prepared");
+  const size_t f = (size_t)(&fp - m->flows.data());
+  const int block = (int)(f / m->cfg.n_flow);
+  tc::LayerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nseg = g.nseg;
+  for (int s = 0; s < g.nseg; ++s) {
+    const int ai = act_index(p->w, g.seg[s].A);
+    FWN_CHECK(ai >= 0, "tc_run_layer: segment %d does not read a planned workspace buffer", s);
+    a.mapA[s] = p->act[(size_t)block * 8 + ai];
+    a.shift[s] = g.seg[s].shift;
+    const int K16 = (g.seg[s].K + 15) / 16 * 16;
+    a.nchunk[s] = (K16 + tc::BK - 1) / tc::BK;
+    a.last_ksteps[s] = (K16 - (a.nchunk[s] - 1) * tc::BK) / tc::UMMA_K;
+    a.wk0[s] = g.seg[s].koff;
+  }
+  a.mapWg = p->wmap[f * GEMM_IDS + GEMM_GATE0 + layer];
+  a.mapWr = p->wmap[f * GEMM_IDS + GEMM_RS0 + layer];
+  auto act_map = [&](const void* ptr, CUtensorMap* dst) -> bool {
+    const int ai = ptr ? act_index(p->w, ptr) : -1;
+    if (ai < 0) return false;
+    *dst = p->act[(size_t)block * 8 + ai];
+    return true;
+  };
+  auto store_map = [&](const void* ptr, CUtensorMap* dst) -> bool {
+    const int ai = ptr ? act_index(p->w, ptr) : -1;
+    if (ai < 0 || ai >= 5) return false;
+    *dst = p->st32[(size_t)block * 5 + ai];
+    return true;
+  };
+  a.has_res = r.e.has_res ? 1 : 0;
+  if (a.has_res) {
+    FWN_CHECK(store_map(r.e.out0, &a.mapOutH) && act_map(r.e.in0, &a.mapIn), "tc_run_layer: residual buffers are not planned buffers");
+    a.has_in = 1;
+  } else if (r.e.in1) {
+    FWN_CHECK(act_map(r.e.in1, &a.mapIn), "tc_run_layer: skip input is not a planned buffer");
+    a.has_in = 1;
+  }
+  FWN_CHECK(store_map(r.e.out1, &a.mapOutS), "tc_run_layer: skip output is not a planned buffer");
+  a.relu = r.e.relu;
+  a.fp16 = m->cfg.precision == FWN_MIXED_FP16 ? 1 : 0;
+  a.B = g.B;
+  a.Ti = g.Ti;
+  a.tiles_per_utt = (g.Ti + tc::BM - 1) / tc::BM;
+  a.gate_bias = g.e.bias;
+  a.rs_bias = r.e.bias;
+  a.pc = reinterpret_cast<const float*>(g.e.in0);
+  a.pc_ld = g.e.ld;
+  return tc::launch_layer(a, st);
 }
 
 // Stand-alone mixed-precision conv (per-op entry fwn_conv1d_bf16): y = [relu](conv(x, w) + bias), bf16 in/out.

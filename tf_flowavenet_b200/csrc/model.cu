@@ -857,6 +857,15 @@ static bool front_direct_enabled() {
   }
   return v == 1;
 }
+// FWN_FUSE_LAYER=0 runs every ResBlock layer as two launches (gate GEMM, res|skip GEMM) instead of the fused layer kernel
+static bool layer_fusion_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_FUSE_LAYER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static bool fp32_front_on_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -938,10 +947,6 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
       g.e.in0 = w.pc[fp.cond_half] + (size_t)(fp.ahead_slot + n) * 2 * F;
       g.e.ld = ca.N;
     }
-    prof_begin(m, PROF_GATE, 2.0 * rows * (3 * F + (fp.ahead ? 0 : fp.Kc)) * 2 * F, st);
-    if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
-    prof_end(m, st);
-
     const bool last = n == L - 1;
     GemmArgs r = {};
     r.B = B; r.Ti = Ti;
@@ -950,9 +955,21 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     r.W = fp.rs_w[n]; r.ldw = fp.rs_ld[n]; r.N = last ? F : 2 * F;
     r.e.bias = fp.rs_b[n]; r.e.F = F; r.e.has_res = !last; r.e.relu = last;
     r.e.in0 = hin; r.e.out0 = hout; r.e.in1 = n > 0 ? w.s : nullptr; r.e.out1 = w.s;
-    prof_begin(m, PROF_RES_SKIP, 2.0 * rows * F * r.N, st);
-    if (run_gemm(m, r, EPI_RES_SKIP, GEMM_RS0 + n, fp, st)) return 1;
-    prof_end(m, st);
+    const double gate_flop = 2.0 * rows * (3 * F + (fp.ahead ? 0 : fp.Kc)) * 2 * F, rs_flop = 2.0 * rows * F * r.N;
+    if (bf16 && (m->fuse_layer < 0 ? layer_fusion_enabled() : m->fuse_layer != 0) && tc_layer_supported(m, g, r)) {
+      // gate GEMM -> tanh*sigmoid -> res|skip 1x1 in one launch: o stays in shared memory (layer_tc.cu)
+      prof_begin(m, PROF_GATE, gate_flop + rs_flop, st);
+      m->launches++;
+      if (tc_run_layer(m, g, r, n, fp, st)) return 1;
+      prof_end(m, st);
+    } else {
+      prof_begin(m, PROF_GATE, gate_flop, st);
+      if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
+      prof_end(m, st);
+      prof_begin(m, PROF_RES_SKIP, rs_flop, st);
+      if (run_gemm(m, r, EPI_RES_SKIP, GEMM_RS0 + n, fp, st)) return 1;
+      prof_end(m, st);
+    }
     std::swap(hin, hout);
   }
   {

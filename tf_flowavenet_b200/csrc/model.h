@@ -97,6 +97,8 @@ struct Model {
   bool train_exact_fwd = false, force_simt = false;
   // training compute dtype: false = fp32-accurate (split engine), true = bf16 operands / tape on the tcgen05 engine (train16.cu)
   bool train_bf16 = false;
+  // mixed inference passes: 1 = fused ResBlock-layer kernel (layer_tc.cu), 0 = gate GEMM + res|skip GEMM as two launches, -1 = FWN_FUSE_LAYER / default
+  int fuse_layer = -1;
   bool packed = false, rev_ok = false;
   char* pack = nullptr;
   size_t pack_bytes = 0;
@@ -150,5 +152,8 @@ void model_drop_graphs(Model* m);
 int prepare_engine(Model* m, const Workspace& w, int B, int T, cudaStream_t st);
 int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPack& fp, cudaStream_t st);
 void engine_free(Model* m);
+// fused ResBlock layer on the tcgen05 engine (gemm_tc.cu / layer_tc.cu): gate GEMM `g` + res|skip 1x1 `r` of layer `layer`
+bool tc_layer_supported(const Model* m, const GemmArgs& g, const GemmArgs& r);
+int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st);
 
 }  // namespace fwn

@@ -444,6 +444,10 @@ class FloWaveNet:
     def last_launches(self):
         return _lib.lib().fwn_last_launches(self._h)
 
+    def set_layer_fusion(self, mode):
+        """Mixed-precision passes: 1 = fused ResBlock-layer kernel, 0 = gate GEMM + res|skip GEMM as two launches, -1 = default."""
+        _lib.check(_lib.lib().fwn_set_layer_fusion(self._h, int(mode)))
+
     # host-buffer entry points (numpy / pinned torch CPU tensors): the end-to-end call of synthesize.py:44-46
     def _check_host(self, a, c, g, what):
         """Same validation as _check_xc / _check_g, for HOST buffers: float32, contiguous, [B,T,1] / [B,T/hop,mels] / int32 [B]."""
