@@ -534,11 +534,13 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
     FWN_CUDA(cudaMemsetAsync(trace_buf, 0, (L_TRACE_TILES * 4 * L_TRACE_K + L_TRACE_TILES) * sizeof(long long), st));
     a.trace = trace_buf;
   }
-  // FWN_LAYER_CLUSTER = 2 (one CTA pair per cluster) | 4 (two pairs sharing multicast weight loads)
+  // FWN_LAYER_CLUSTER = 2 (default: one CTA pair per cluster) | 4 (EXPERIMENTAL: two pairs sharing multicast weight loads; parity-clean
+  // on small launches, no faster with the epilogue traffic switched off (26.9 vs 28.6 ms per C3 pass) and it stalls on full-size
+  // launches -- kept for diagnostics only)
   static int cl_size = 0, max_cl4 = 0;
   if (!cl_size) {
     const char* e = getenv("FWN_LAYER_CLUSTER");
-    cl_size = (e && e[0] == '2') ? 2 : 4;
+    cl_size = (e && e[0] == '4') ? 4 : 2;
     FWN_CUDA(cudaFuncSetAttribute(layer_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
     FWN_CUDA(cudaFuncSetAttribute(layer_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
     if (cl_size == 4) {   // how many 4-CTA clusters fit at once (GPCs whose SM count is not a multiple of 4 leave SMs over)

@@ -956,7 +956,12 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     r.e.bias = fp.rs_b[n]; r.e.F = F; r.e.has_res = !last; r.e.relu = last;
     r.e.in0 = hin; r.e.out0 = hout; r.e.in1 = n > 0 ? w.s : nullptr; r.e.out1 = w.s;
     const double gate_flop = 2.0 * rows * (3 * F + (fp.ahead ? 0 : fp.Kc)) * 2 * F, rs_flop = 2.0 * rows * F * r.N;
-    if (bf16 && (m->fuse_layer < 0 ? layer_fusion_enabled() : m->fuse_layer != 0) && tc_layer_supported(m, g, r)) {
+    // default: fuse when the launch has at least two waves of row-tile pairs -- below that the fused kernel (one CTA pair walks
+    // G0, G1, R, K of its rows in sequence) loses to two launches that spread the column tiles over twice as many SMs
+    // (C1, 1 s / batch 1: 4.42 ms fused vs 3.62 ms per pass)
+    const int64_t row_pairs = ((int64_t)B * ((Ti + 127) / 128) + 1) / 2;
+    const bool fuse = m->fuse_layer < 0 ? (layer_fusion_enabled() && row_pairs >= 2 * (num_sms() / 2)) : m->fuse_layer != 0;
+    if (bf16 && fuse && tc_layer_supported(m, g, r)) {
       // gate GEMM -> tanh*sigmoid -> res|skip 1x1 in one launch: o stays in shared memory (layer_tc.cu)
       prof_begin(m, PROF_GATE, gate_flop + rs_flop, st);
       m->launches++;

@@ -2,7 +2,7 @@
 # usage (GPU box): bash tools/layer_ab.sh "<env assignments>" ...   -- C3 pass time and the fused-layer family time for each setting
 mkdir -p gpurun_out
 for cfg in "$@"; do
-  env $cfg timeout 200 python bench.py --workload c3 --steps 6 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ab.json 2> gpurun_out/ab.err
+  env $cfg timeout 200 python bench.py --workload ${WL:-c3} --steps ${STEPS:-6} --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/ab.json 2> gpurun_out/ab.err
   python - "$cfg" <<'PY'
 import json, sys
 try:
