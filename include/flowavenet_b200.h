@@ -139,9 +139,11 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
  * 3 terms (a1w1 + a1w2 + a2w1) keep ~2^-16..2^-18 per product at half the tensor work (default for the training step; gradients
  * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
-/* Mixed-precision passes: how a ResBlock layer (modules.py:113-128) is launched.  1 = one fused kernel per layer (gate GEMM ->
- * tanh*sigmoid -> res|skip 1x1 with the gated tile kept in shared memory), 0 = two launches with the gated activations round-tripping
- * through HBM, -1 = default (fused; environment FWN_FUSE_LAYER=0 disables).  Both give bit-identical results. */
+/* Mixed-precision passes: how the coupling WaveNet (modules.py:113-128, 161-186) is launched.  1 = fused kernels: one per ResBlock
+ * layer (gate GEMM -> tanh*sigmoid -> res|skip 1x1, the gated tile kept in shared memory) and one for the tail (final 1x1 + ReLU ->
+ * ZeroConv1d -> ActNorm / affine coupling on x); 0 = one launch per GEMM with the intermediate activations round-tripping through
+ * HBM; -1 = default (fused where it pays: large launches for the layer kernel; FWN_FUSE_LAYER=0 / FWN_FUSE_TAIL=0 disable).
+ * The layer kernel is bit-identical to its two launches; the tail kernel rounds the same 16-bit u. */
 int fwn_set_layer_fusion(fwn_handle h, int mode);
 /* Compute precision of the training step (the model keeps fp32 master variables either way, utils.py:3-31):
  *   FWN_FP32        fp32-accurate GEMMs (3-way bf16 split on the tensor cores) -- the parity mode (default)

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "layer_tc.cuh"
+#include "tail_tc.cuh"
 #include "model.h"
 #include "tc_ptx.cuh"
 
@@ -1029,6 +1030,38 @@ int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, cons
   a.pc = reinterpret_cast<const float*>(g.e.in0);
   a.pc_ld = g.e.ld;
   return tc::launch_layer(a, st);
+}
+
+// Fused WaveNet tail (tail_tc.cu): final 1x1 `f` (+ReLU) and the zero conv + affine coupling `z` in one launch; u never leaves the SM.
+// Supported: F = 256 and at most 32 zero-conv columns (blocks with C_x <= 32); deeper blocks take the two-launch path.
+bool tc_tail_supported(const Model* m, const GemmArgs& f, const GemmArgs& z) {
+  if (!m->tc || m->cfg.filter_size != 256) return false;
+  if (z.e.out1 || z.N > 32 || !f.e.relu) return false;
+  return true;
+}
+int tc_run_tail(Model* m, const GemmArgs& f, const GemmArgs& z, const FlowPack& fp, cudaStream_t st) {
+  TcPlan* p = m->tc;
+  FWN_CHECK(p, "tcgen05 engine not prepared");
+  const size_t fi = (size_t)(&fp - m->flows.data());
+  const int block = (int)(fi / m->cfg.n_flow);
+  tc::TailArgs a;
+  memset(&a, 0, sizeof(a));
+  const int ai = act_index(p->w, f.seg[0].A);
+  FWN_CHECK(ai >= 0, "tc_run_tail: the final conv does not read a planned workspace buffer");
+  a.mapS = p->act[(size_t)block * 8 + ai];
+  a.mapWf = p->wmap[fi * GEMM_IDS + GEMM_FINAL];
+  a.mapWz = p->wmap[fi * GEMM_IDS + GEMM_ZERO];
+  FWN_CHECK(p->wbn[fi * GEMM_IDS + GEMM_FINAL] == 128, "tc_run_tail: final-conv weight map has the wrong box");
+  a.B = f.B;
+  a.Ti = f.Ti;
+  a.tiles_per_utt = (f.Ti + tc::BM - 1) / tc::BM;
+  a.Nz = z.N;
+  a.NzBox = std::min(p->wbn[fi * GEMM_IDS + GEMM_ZERO], (z.N + 15) / 16 * 16);
+  FWN_CHECK(a.NzBox == 16 || a.NzBox == 32, "tc_run_tail: zero conv too wide (%d)", a.NzBox);
+  a.fp16 = m->cfg.precision == FWN_MIXED_FP16 ? 1 : 0;
+  a.final_bias = f.e.bias;
+  a.e = z.e;
+  return tc::launch_tail(a, st);
 }
 
 // Stand-alone mixed-precision conv (per-op entry fwn_conv1d_bf16): y = [relu](conv(x, w) + bias), bf16 in/out.

@@ -866,6 +866,15 @@ static bool layer_fusion_enabled() {
   }
   return v == 1;
 }
+// FWN_FUSE_TAIL=0 runs the WaveNet tail as two launches (final conv, zero conv + affine) instead of the fused tail kernel
+static bool tail_fusion_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_FUSE_TAIL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static bool fp32_front_on_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -984,26 +993,34 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     g.nseg = 1;
     g.W = fp.final_w; g.ldw = fp.final_ld; g.N = F;
     g.e.bias = fp.final_b; g.e.out0 = w.u; g.e.ld = F; g.e.relu = 1; g.e.F = F;
-    prof_begin(m, PROF_FINAL, 2.0 * rows * F * F, st);
-    if (run_gemm(m, g, EPI_PLAIN, GEMM_FINAL, fp, st)) return 1;
-    prof_end(m, st);
-  }
-  {
-    GemmArgs g = {};
-    g.B = B; g.Ti = Ti;
-    g.seg[0] = Seg{w.u, F, 0, F, 0};
-    g.nseg = 1;
-    g.W = fp.zero_w; g.ldw = fp.zero_ld; g.N = 2 * fp.nq;
-    g.e.bias = fp.zero_b; g.e.F = F;
-    g.e.X = X; g.e.Cx = fp.Cx; g.e.nq = fp.nq; g.e.a_off = fp.a_off; g.e.b_off = fp.b_off;
-    g.e.an_b = fp.an_b; g.e.an_s = reverse ? fp.an_is : fp.an_s;
-    g.e.logdet_acc = reverse ? nullptr : w.sums;
-    g.e.reverse = reverse;
-    g.e.pairs_adjacent = fp.pairs_adjacent;
-    g.e.b_odd = fp.b_odd;
-    prof_begin(m, PROF_ZERO_AFFINE, 2.0 * rows * F * (c.affine ? fp.Cx : fp.nq), st);
-    if (run_gemm(m, g, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
-    prof_end(m, st);
+    GemmArgs z = {};
+    z.B = B; z.Ti = Ti;
+    z.seg[0] = Seg{w.u, F, 0, F, 0};
+    z.nseg = 1;
+    z.W = fp.zero_w; z.ldw = fp.zero_ld; z.N = 2 * fp.nq;
+    z.e.bias = fp.zero_b; z.e.F = F;
+    z.e.X = X; z.e.Cx = fp.Cx; z.e.nq = fp.nq; z.e.a_off = fp.a_off; z.e.b_off = fp.b_off;
+    z.e.an_b = fp.an_b; z.e.an_s = reverse ? fp.an_is : fp.an_s;
+    z.e.logdet_acc = reverse ? nullptr : w.sums;
+    z.e.reverse = reverse;
+    z.e.pairs_adjacent = fp.pairs_adjacent;
+    z.e.b_odd = fp.b_odd;
+    const double final_flop = 2.0 * rows * F * F, zero_flop = 2.0 * rows * F * (c.affine ? fp.Cx : fp.nq);
+    const bool fuse_tail = m->fuse_layer < 0 ? tail_fusion_enabled() : m->fuse_layer != 0;
+    if (bf16 && fuse_tail && tc_tail_supported(m, g, z)) {
+      // final 1x1 + ReLU -> zero conv -> ActNorm / affine coupling on x in one launch: u stays in shared memory (tail_tc.cu)
+      prof_begin(m, PROF_FINAL, final_flop + zero_flop, st);
+      m->launches++;
+      if (tc_run_tail(m, g, z, fp, st)) return 1;
+      prof_end(m, st);
+    } else {
+      prof_begin(m, PROF_FINAL, final_flop, st);
+      if (run_gemm(m, g, EPI_PLAIN, GEMM_FINAL, fp, st)) return 1;
+      prof_end(m, st);
+      prof_begin(m, PROF_ZERO_AFFINE, zero_flop, st);
+      if (run_gemm(m, z, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
+      prof_end(m, st);
+    }
   }
   return 0;
 }

@@ -155,5 +155,8 @@ void engine_free(Model* m);
 // fused ResBlock layer on the tcgen05 engine (gemm_tc.cu / layer_tc.cu): gate GEMM `g` + res|skip 1x1 `r` of layer `layer`
 bool tc_layer_supported(const Model* m, const GemmArgs& g, const GemmArgs& r);
 int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st);
+// fused WaveNet tail (gemm_tc.cu / tail_tc.cu): final 1x1 `f` + zero conv / affine coupling `z`
+bool tc_tail_supported(const Model* m, const GemmArgs& f, const GemmArgs& z);
+int tc_run_tail(Model* m, const GemmArgs& f, const GemmArgs& z, const FlowPack& fp, cudaStream_t st);
 
 }  // namespace fwn
