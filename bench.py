@@ -439,23 +439,32 @@ def run_pass(args, dist, workload, with_cpu=True, steps=None):
     g_ms, g_n, g_flop = prof["gate_gemm"]
     ach = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     mixed = dtype != "float32"
-    roof = {"kernel": "tc_gemm_kernel<EPI_GATE,256> (dilated conv k=3 + cond 1x1 + tanh*sigmoid)" if mixed else
+    # mixed modes, large launches: each ResBlock layer is ONE kernel (gate GEMM -> tanh*sigmoid -> res|skip 1x1, csrc/layer_tc.cu); its
+    # family time and FLOP count then cover both GEMMs and the res_skip family is empty.  Small launches keep the two-launch path.
+    fused = mixed and prof["res_skip_gemm"][1] < prof["gate_gemm"][1]
+    roof = {"kernel": ("layer_kernel<2> (fused ResBlock layer: dilated conv k=3 + cond 1x1 + tanh*sigmoid + res|skip 1x1; deep-block launches: "
+                       "tc_gemm_kernel<EPI_GATE,256> + <EPI_RES_SKIP>)" if fused else
+                       "tc_gemm_kernel<EPI_GATE,256> (dilated conv k=3 + cond 1x1 + tanh*sigmoid)") if mixed else
             ("simt_gemm_kernel<EPI_GATE>" if os.environ.get("FWN_FP32_ENGINE") == "simt" else
              "tc3_gemm_kernel<EPI_GATE,128> (fp32 parity mode: 6 bf16 MMA terms per product, so <= 1/6 of the bf16 peak is attainable)"),
             "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
             "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk["src"], "traffic": None,
             "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / ms_prof,
-            "instrumented_ms_per_step": ms_prof / steps,
+            "instrumented_ms_per_step": ms_prof / steps, "fused_layers": bool(fused),
             "families": {k: {"ms": v[0], "launches": v[1], "achieved": (v[2] / (v[0] * 1e-3) / (1e9 if k == "upsample" else 1e12)) if v[0] > 0 else 0.0,
                              "unit": "GB/s" if k == "upsample" else "TFLOP/s"} for k, v in prof.items()},
             "whole_pass_tflops": value * MFLOP_PER_SAMPLE[preset] * 1e6 / 1e12 / world}
-    tp = os.path.join(ROOT, "profiles", "r1_gate_traffic.json")
+    if fused:
+        roof["note"] = ("gate_gemm family = the fused layer kernel (gate + res|skip FLOPs, HBM-side epilogue I/O included); final_conv family = the "
+                        "fused tail kernel (final 1x1 + zero conv + affine).  With the 1x1 epilogue I/O switched off the layer kernel runs at the "
+                        "power-capped tensor rate (profiles/r2_ncu_fused.md)")
+    tp = os.path.join(ROOT, "profiles", "r2_layer_traffic.json" if fused else "r1_gate_traffic.json")
     if mixed and workload == "c3" and os.path.exists(tp):
         tj = json.load(open(tp))
         # DRAM bytes of ONE ncu --set full capture of this kernel (its block-0 launch), next to that launch's algorithmic bytes:
         # a committed capture, NOT re-measured by this run
         roof["traffic"] = tj["traffic_bytes_per_launch"]
-        roof["traffic_source"] = "static ncu capture (round 1, %s): one block-0 launch on one GPU" % tj["source"]
+        roof["traffic_source"] = "static ncu capture (%s): one block-0 launch on one GPU" % tj["source"]
         roof["traffic_detail"] = {k: tj[k] for k in ("launch", "source", "algorithmic_bytes_per_launch", "algorithmic_flop_per_launch")}
     ups = prof["upsample"]
     if ups[0] > 0:
@@ -526,7 +535,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="default invocation: skip the c4s / c5 legs")
     ap.add_argument("--dtype", default=None, choices=["bfloat16", "float16"], help="operand type of the mixed-precision workloads")
-    ap.add_argument("--train-dtype", default="float32", choices=["bfloat16", "float32"], help="c5: compute dtype of the training step")
+    ap.add_argument("--train-dtype", default="bfloat16", choices=["bfloat16", "float32"],
+                    help="c5: compute dtype of the training step (BASELINE config 5 is bf16; float32 = the fp32-accurate parity mode)")
     ap.add_argument("--split-terms", type=int, default=3, choices=[3, 6], help="c5 in float32: bf16 products per fp32 product in the training GEMMs")
     args = ap.parse_args()
     dist = Dist()
