@@ -294,8 +294,9 @@ int front_conv(const FrontArgs& a, bool bf16_out, cudaStream_t st) {
 // (+ halo) are gathered once into shared memory -- the NEXT tile's inputs are already in flight in registers while this tile is
 // computed --, then each warp produces 8 rows: a lane owns 8 channels (its 3 nq x 8 weights live in registers), the 3 nq inputs of
 // a row are broadcast shared-memory reads, and a row leaves as 32 contiguous 16-byte stores, 8 independent rows in flight per warp.
-constexpr int FD_ROWS = 64;
-template <int NQ, typename T16>
+// Rows per tile: 256 / 128 / 64 for nq = 1 / 2 / 4 -- one tile's compute (~3 k cycles) then covers the DRAM latency of the next tile's
+// inputs, which are requested one tile ahead (with 64-row tiles every tile waited ~1.5 k cycles for them: 0.48 of the HBM write rate).
+template <int NQ, typename T16, int FD_ROWS>
 __global__ void __launch_bounds__(256, 2) front_direct_kernel(const FrontArgs a, int lo, int hi, int tiles_per_utt, int n_tiles) {
   constexpr int SPAN = FD_ROWS + 64;   // rows [t0 + lo, t0 + FD_ROWS + hi) with -32 <= lo <= 0 <= hi <= 32
   constexpr int PER = (SPAN * NQ + 255) / 256;
@@ -383,13 +384,19 @@ int front_direct(const FrontArgs& a, bool fp16, cudaStream_t st) {
   FWN_CHECK(front_direct_supported(a), "front_direct: needs F = 256, nq in {1, 2, 4} and |shift| <= 32");
   int lo = 0, hi = 0;
   for (int k = 0; k < 3; ++k) { lo = std::min(lo, a.shift[k]); hi = std::max(hi, a.shift[k]); }
-  const int tiles_per_utt = (a.Ti + FD_ROWS - 1) / FD_ROWS;
-  const int n_tiles = a.B * tiles_per_utt;
-  const int grid = std::min(n_tiles, num_sms() * 2);
-#define FWN_FD(NQ)                                                                                                   \
-  if (fp16) front_direct_kernel<NQ, __half><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);                \
-  else front_direct_kernel<NQ, __nv_bfloat16><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles)
-  if (a.nq == 1) { FWN_FD(1); } else if (a.nq == 2) { FWN_FD(2); } else { FWN_FD(4); }
+#define FWN_FD(NQ, ROWS)                                                                                             \
+  {                                                                                                                  \
+    const int tiles_per_utt = (a.Ti + ROWS - 1) / ROWS;                                                              \
+    const int n_tiles = a.B * tiles_per_utt;                                                                         \
+    const int grid = std::min(n_tiles, num_sms() * 2);                                                               \
+    if (fp16) front_direct_kernel<NQ, __half, ROWS><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);        \
+    else front_direct_kernel<NQ, __nv_bfloat16, ROWS><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);      \
+  }
+  // big tiles only when they still give every SM several tiles; short inputs keep 64-row tiles (more blocks in flight)
+  const bool big = (int64_t)a.B * a.Ti >= (int64_t)256 * 4 * num_sms();
+  if (a.nq == 1) { if (big) FWN_FD(1, 256) else FWN_FD(1, 64) }
+  else if (a.nq == 2) { if (big) FWN_FD(2, 128) else FWN_FD(2, 64) }
+  else FWN_FD(4, 64)
 #undef FWN_FD
   FWN_LAUNCH_CHECK();
   return 0;

@@ -516,26 +516,30 @@ __global__ void upsample_warp_kernel(const float* __restrict__ in, const float* 
 // store instruction covers 512 contiguous bytes.  The 2 x 10 inputs a thread needs come from the (tiny, L1-resident) stage input:
 // an input frame is re-used by the s output steps it feeds.  No shared-memory staging, no warp synchronisation: the kernel runs at
 // the write bandwidth of its output.
-template <typename TOut, bool SPLIT>
+// IT = index type of the flat chunk index: 32-bit whenever the tensor allows it (64-bit divisions cost ~100 instructions each, and
+// five of them per 16-byte store made the kernel issue-bound at 0.2 of the HBM rate).
+template <typename TOut, bool SPLIT, typename IT>
 __global__ void __launch_bounds__(256) upsample_chunk_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias_p,
                                                              TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
   extern __shared__ float sw[];  // [2s*3]
   for (int i = threadIdx.x; i < 2 * s * 3; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const int To = Tm * s, half = mels / 2;
+  const IT To = (IT)Tm * (IT)s;
+  const int half = mels / 2;
   const int pm = SPLIT ? half : mels;            // mel bins per output row of one plane
-  const int gpr = pm / 8;                        // 8-mel chunks per row
-  const int64_t rows = (int64_t)B * To;
-  const int64_t per_plane = rows * gpr;
-  const int64_t total = per_plane * (SPLIT ? 2 : 1);
+  const IT gpr = (IT)(pm / 8);                   // 8-mel chunks per row
+  const IT rows = (IT)B * To;
+  const IT per_plane = rows * gpr;
+  const IT total = per_plane * (SPLIT ? 2 : 1);
   const float bias = __ldg(bias_p);
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int pl = SPLIT ? (int)(idx / per_plane) : 0;
-    const int64_t rem = idx - (int64_t)pl * per_plane;
-    const int64_t bt = rem / gpr;
+  for (IT idx = (IT)blockIdx.x * (IT)blockDim.x + (IT)threadIdx.x; idx < total; idx += (IT)gridDim.x * (IT)blockDim.x) {
+    const int pl = (SPLIT && idx >= per_plane) ? 1 : 0;
+    const IT rem = idx - (pl ? per_plane : (IT)0);
+    const IT bt = rem / gpr;
     const int gi = (int)(rem - bt * gpr);
-    const int b = (int)(bt / To), i = (int)(bt - (int64_t)b * To);
-    const int q = i + s / 2, r = q % s, j0 = q / s;                 // taps kh = r (frame j0) and r + s (frame j0 - 1)
+    const IT bb = bt / To;
+    const int b = (int)bb, i = (int)(bt - bb * To);
+    const int q = i + s / 2, j0 = q / s, r = q - j0 * s;           // taps kh = r (frame j0) and r + s (frame j0 - 1)
     const int m0 = pl * half + gi * 8;                             // first mel bin of the chunk
     float x1[10], x0[10];                                          // frames j0 / j0-1, mel bins m0-1 .. m0+8 (zero outside)
     const float* f1 = in + ((int64_t)b * Tm + j0) * mels;
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(256) upsample_chunk_kernel(const float* __rest
       v = fmaf(x0[j + 2], c0, fmaf(x0[j + 1], c1, fmaf(x0[j], c2, v)));
       acc[j] = fmaxf(v, 0.4f * v);
     }
-    TOut* dst = (SPLIT && pl == 1 ? out1 : out0) + bt * pm + gi * 8;
+    TOut* dst = (SPLIT && pl == 1 ? out1 : out0) + (int64_t)bt * pm + gi * 8;
     if constexpr (sizeof(TOut) == 2) {
       *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<TOut>(acc[0], acc[1]), pack2<TOut>(acc[2], acc[3]),
                                                   pack2<TOut>(acc[4], acc[5]), pack2<TOut>(acc[6], acc[7]));
@@ -594,8 +598,14 @@ int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* o
   if (!use_warp_kernel && al16 && mels % 8 == 0 && (!split || (mels / 2) % 8 == 0)) {
     const int64_t chunks = n / 8;
     const int g2 = (int)std::min<int64_t>(cdiv(chunks, 256), (int64_t)num_sms() * 32);
-    if (split) upsample_chunk_kernel<TOut, true><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
-    else upsample_chunk_kernel<TOut, false><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    const bool small = chunks + (int64_t)g2 * 256 < (int64_t(1) << 31);   // flat chunk index (plus one grid stride) fits 32 bits
+    if (small) {
+      if (split) upsample_chunk_kernel<TOut, true, uint32_t><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+      else upsample_chunk_kernel<TOut, false, uint32_t><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    } else {
+      if (split) upsample_chunk_kernel<TOut, true, int64_t><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+      else upsample_chunk_kernel<TOut, false, int64_t><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+    }
     FWN_LAUNCH_CHECK();
     return 0;
   }
