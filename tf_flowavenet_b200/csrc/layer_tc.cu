@@ -102,6 +102,26 @@ __device__ __forceinline__ void umma_chunk_commit_mask(uint32_t tmem_d, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(ksteps), "r"(bar), "h"(mask)
       : "memory");
 }
+// the same four MMAs without the commit (two weight boxes share one pipeline stage in the 1x1 ops)
+__device__ __forceinline__ void umma_chunk_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe, pacc, pt;\n"
+      ".reg .b64 da, db;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 pacc, %4, 0;\n"
+      "setp.eq.u32 pt, 0, 0;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pacc;\n"
+      "add.u64 da, %1, 2;\n add.u64 db, %2, 2;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n"
+      "add.u64 da, %1, 4;\n add.u64 db, %2, 4;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n"
+      "add.u64 da, %1, 6;\n add.u64 db, %2, 6;\n"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
   asm volatile(
       "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
@@ -268,12 +288,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
             for (int sub = 0; sub < 4; ++sub) stage_in(it, sub);
           // 1x1 ops: only the weight half-boxes stream; the A operand is the o tile
           const int n0 = ((a.has_res && kind == OP_SKIP) ? 256 : 0) + rank * 128;
-          for (int kc = 0; kc < 4; ++kc) {
+          for (int kc = 0; kc < 4; kc += 2) {   // two K chunks of weight half-boxes per stage (a stage has room for an A and a B box)
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * L_STAGE_BYTES;
-            if (leader) mbar_expect_tx(full_bar + stage, 2 * A_BYTES);
-            if (CL == 2) tma_load_2d_2sm(sa + A_BYTES, &a.mapWr, full_bar + stage, kc * BK, n0);
-            else if (pr == 0) tma_load_2d_2sm_mc(sa + A_BYTES, &a.mapWr, full_bar + stage, kc * BK, n0, (uint16_t)(5u << rank));
+            if (leader) mbar_expect_tx(full_bar + stage, 2 * L_STAGE_BYTES);
+            if (CL == 2) {
+              tma_load_2d_2sm(sa, &a.mapWr, full_bar + stage, kc * BK, n0);
+              tma_load_2d_2sm(sa + A_BYTES, &a.mapWr, full_bar + stage, (kc + 1) * BK, n0);
+            } else if (pr == 0) {
+              tma_load_2d_2sm_mc(sa, &a.mapWr, full_bar + stage, kc * BK, n0, (uint16_t)(5u << rank));
+              tma_load_2d_2sm_mc(sa + A_BYTES, &a.mapWr, full_bar + stage, (kc + 1) * BK, n0, (uint16_t)(5u << rank));
+            }
             if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -311,17 +336,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
             }
           }
         } else {
-          for (int kc = 0; kc < 4; ++kc) {
-            if ((kc & 1) == 0) {   // o channels [0,128) come from G0's epilogue, [128,256) from G1's
-              mbar_wait_cluster(o_full + (kc >> 1), (uint32_t)it & 1);
-              tcgen05_fence_after();
-              L_TRACE(2 + (kc >> 1));
-            }
+          for (int kc = 0; kc < 4; kc += 2) {
+            // o channels [0,128) come from G0's epilogue, [128,256) from G1's
+            mbar_wait_cluster(o_full + (kc >> 1), (uint32_t)it & 1);
+            tcgen05_fence_after();
+            L_TRACE(2 + (kc >> 1));
             mbar_wait(full_bar + stage, phase);
             tcgen05_fence_after();
-            const uint32_t sa = o0 + (uint32_t)kc * A_BYTES, sb = stage0 + (uint32_t)stage * L_STAGE_BYTES + A_BYTES;
-            const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF), bdesc = desc_hi | (uint64_t)((sb >> 4) & 0x3FFF);
-            umma_chunk_commit_mask(tmem_d, adesc, bdesc, idesc, accumulate, 4u, smem_u32(empty_bar + stage), all_mask);
+            const uint32_t sa = o0 + (uint32_t)kc * A_BYTES, sb = stage0 + (uint32_t)stage * L_STAGE_BYTES;
+            umma_chunk_pair(tmem_d, desc_hi | (uint64_t)((sa >> 4) & 0x3FFF), desc_hi | (uint64_t)((sb >> 4) & 0x3FFF), idesc, accumulate);
+            umma_chunk_commit_mask(tmem_d, desc_hi | (uint64_t)(((sa + A_BYTES) >> 4) & 0x3FFF), desc_hi | (uint64_t)(((sb + A_BYTES) >> 4) & 0x3FFF),
+                                   idesc, 1u, 4u, smem_u32(empty_bar + stage), all_mask);
             accumulate = 1;
             if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
           }

@@ -45,7 +45,7 @@ def main():
     x, c = synthetic_inputs(hop, 80, B, n_frames, 1239, "x")
     g = torch.zeros(B, dtype=torch.int32).cuda()
     x, c = torch.from_numpy(x).cuda(), torch.from_numpy(c).cuda()
-    tr = Trainer(net, split_terms=3)
+    tr = Trainer(net, split_terms=3, compute_dtype=os.environ.get("TRAIN_DTYPE", "bfloat16"))
     tr.train_step(x, c, g, init=True)
     tr.train_step(x, c, g)
     torch.cuda.synchronize()
