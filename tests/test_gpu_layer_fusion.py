@@ -54,3 +54,27 @@ def test_fused_layer_bit_equal_to_two_launches(n_block, n_flow, n_layer, scales,
     # log_p / log-det are double-precision atomic sums of identical terms: equal up to summation order
     assert abs(out[0][0] - out[1][0]) <= 1e-6 * max(1.0, abs(out[0][0])) and abs(out[0][1] - out[1][1]) <= 1e-6 * max(1.0, abs(out[0][1]))
     assert out[1][4] < out[0][4]   # the fused path really ran (fewer launches)
+
+
+def test_front_direct_tile_sizes_agree(monkeypatch):
+    """front_direct_kernel (csrc/conv_simt.cu; modules.py:164-165 front conv straight from the flow variable) picks 256- / 128-row tiles
+    for long inputs and 64-row tiles otherwise: both on the same input, bit for bit (ragged tiles, utterance borders inside a tile)."""
+    import tf_flowavenet_b200 as P
+    hp = O.HP(n_block=5, n_flow=6, n_layer=2, num_mels=80, upsample_scales=(8, 12))
+    params = O.synthetic_params(hp, 15)
+    x, c = O.synthetic_inputs(hp, 3, 41, 16, "x")     # block 0: 3 x 1968 rows = 7.7 tiles of 256, block 1: 3 x 984 rows
+    z_in, _ = O.synthetic_inputs(hp, 3, 41, 17, "z")
+    net = P.FloWaveNet(P.HParams(n_block=5, n_flow=6, n_layer=2, num_mels=80, upsample_scales=[8, 12], dtype="bfloat16"), variables=P.VariableStore())
+    net.load_variables({k: v.numpy() for k, v in params.items()})
+    xd, cd, zd = x.cuda(), c.cuda(), z_in.cuda()
+    out = {}
+    for mode in ("small", "big"):
+        monkeypatch.setenv("FWN_FRONT_TILE", mode)
+        net.set_layer_fusion(-1)   # drops the captured graphs: the next passes launch with the new setting
+        for rep in range(2):
+            lp, ld, z = net.forward(xd, cd, return_z=True)
+            xr = net.reverse(zd, cd)
+        torch.cuda.synchronize()
+        out[mode] = (z.clone(), xr.clone())
+    assert torch.isfinite(out["big"][0]).all()
+    assert torch.equal(out["small"][0], out["big"][0]) and torch.equal(out["small"][1], out["big"][1])

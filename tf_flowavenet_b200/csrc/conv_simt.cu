@@ -393,7 +393,8 @@ int front_direct(const FrontArgs& a, bool fp16, cudaStream_t st) {
     else front_direct_kernel<NQ, __nv_bfloat16, ROWS><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);      \
   }
   // big tiles only when they still give every SM several tiles; short inputs keep 64-row tiles (more blocks in flight)
-  const bool big = (int64_t)a.B * a.Ti >= (int64_t)256 * 4 * num_sms();
+  bool big = (int64_t)a.B * a.Ti >= (int64_t)256 * 4 * num_sms();
+  if (const char* e = getenv("FWN_FRONT_TILE")) big = e[0] == 'b';   // "big" / "small": tests run both tile sizes on the same input
   if (a.nq == 1) { if (big) FWN_FD(1, 256) else FWN_FD(1, 64) }
   else if (a.nq == 2) { if (big) FWN_FD(2, 128) else FWN_FD(2, 64) }
   else FWN_FD(4, 64)
