@@ -572,6 +572,66 @@ __global__ void __launch_bounds__(256) upsample_chunk_kernel(const float* __rest
     }
   }
 }
+// Frame-per-thread upsampler: one thread = 8 consecutive mel bins of the s output time steps fed by one pair of input frames
+// (j0 - 1, j0): the 2 x 10 inputs are loaded once and every step costs 48 FMA + one 16-byte store, 4x fewer instructions per byte
+// than one thread per store (which was issue-bound at 0.2 of the HBM rate).  Lanes walk the chunks of a row first, so a store
+// instruction writes runs of pm * 2 contiguous bytes, s rows apart.
+template <typename TOut, bool SPLIT>
+__global__ void __launch_bounds__(256) upsample_frame_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias_p,
+                                                             TOut* __restrict__ out0, TOut* __restrict__ out1, int B, int Tm, int mels, int s) {
+  extern __shared__ float sw[];  // [2s*3]
+  for (int i = threadIdx.x; i < 2 * s * 3; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int half = mels / 2;
+  const int pm = SPLIT ? half : mels;            // mel bins per output row of one plane
+  const uint32_t gpr = (uint32_t)(pm / 8);       // 8-mel chunks per row
+  const uint32_t per_b = (uint32_t)(Tm + 1) * gpr, per_plane = (uint32_t)B * per_b;
+  const uint32_t total = per_plane * (SPLIT ? 2u : 1u);
+  const int To = Tm * s;
+  const float bias = __ldg(bias_p);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int pl = (SPLIT && idx >= per_plane) ? 1 : 0;
+    const uint32_t rem = idx - (pl ? per_plane : 0u);
+    const uint32_t b = rem / per_b, rb = rem - b * per_b;
+    const int j0 = (int)(rb / gpr), gi = (int)(rb - (uint32_t)j0 * gpr);
+    const int m0 = pl * half + gi * 8;
+    float x1[10], x0[10];                          // frames j0 / j0-1, mel bins m0-1 .. m0+8 (zero outside)
+    const float* f1 = in + ((int64_t)b * Tm + j0) * mels;
+    const float* f0 = f1 - mels;
+    const bool v1 = j0 < Tm, v0 = j0 >= 1;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const int mm = m0 - 1 + k;
+      const bool ok = mm >= 0 && mm < mels;
+      x1[k] = (ok && v1) ? __ldg(f1 + mm) : 0.f;
+      x0[k] = (ok && v0) ? __ldg(f0 + mm) : 0.f;
+    }
+    TOut* plane = (SPLIT && pl == 1 ? out1 : out0) + gi * 8;
+    const int i0 = j0 * s - s / 2;                 // output steps i0 .. i0 + s - 1 use taps kh = r (frame j0) and r + s (frame j0 - 1)
+    for (int r = 0; r < s; ++r) {
+      const int i = i0 + r;
+      if (i < 0 || i >= To) continue;
+      const float a0 = sw[r * 3], a1 = sw[r * 3 + 1], a2 = sw[r * 3 + 2];
+      const float c0 = sw[(r + s) * 3], c1 = sw[(r + s) * 3 + 1], c2 = sw[(r + s) * 3 + 2];
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // out[m] = sum_kw in[m + 1 - kw] * w[kh][kw]
+        float v = bias;
+        v = fmaf(x1[j + 2], a0, fmaf(x1[j + 1], a1, fmaf(x1[j], a2, v)));
+        v = fmaf(x0[j + 2], c0, fmaf(x0[j + 1], c1, fmaf(x0[j], c2, v)));
+        acc[j] = fmaxf(v, 0.4f * v);
+      }
+      TOut* dst = plane + ((int64_t)b * To + i) * pm;
+      if constexpr (sizeof(TOut) == 2) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<TOut>(acc[0], acc[1]), pack2<TOut>(acc[2], acc[3]),
+                                                    pack2<TOut>(acc[4], acc[5]), pack2<TOut>(acc[6], acc[7]));
+      } else {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  }
+}
 // weight norm of the [2s,3,1,1] kernel over axes [0,2] => per kw column (convolutional.py:186)
 __global__ void upsample_wn_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int s) {
   int kw = threadIdx.x;
@@ -598,6 +658,15 @@ int upsample_stage_t(const float* in, const float* w, const float* bias, TOut* o
   if (!use_warp_kernel && al16 && mels % 8 == 0 && (!split || (mels / 2) % 8 == 0)) {
     const int64_t chunks = n / 8;
     const int g2 = (int)std::min<int64_t>(cdiv(chunks, 256), (int64_t)num_sms() * 32);
+    static const bool use_chunk_kernel = getenv("FWN_UPSAMPLE_CHUNK") != nullptr;   // the per-store kernel, kept for A/B timing
+    const int64_t frame_threads = (int64_t)B * (Tm + 1) * (mels / 8);
+    if (!use_chunk_kernel && s <= 32 && frame_threads + (int64_t)num_sms() * 32 * 256 < (int64_t(1) << 31)) {
+      const int g3 = (int)std::min<int64_t>(cdiv(frame_threads, 256), (int64_t)num_sms() * 32);
+      if (split) upsample_frame_kernel<TOut, true><<<g3, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+      else upsample_frame_kernel<TOut, false><<<g3, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
+      FWN_LAUNCH_CHECK();
+      return 0;
+    }
     const bool small = chunks + (int64_t)g2 * 256 < (int64_t(1) << 31);   // flat chunk index (plus one grid stride) fits 32 bits
     if (small) {
       if (split) upsample_chunk_kernel<TOut, true, uint32_t><<<g2, 256, smem, st>>>(in, w, bias, out0, out1, B, Tm, mels, s);
