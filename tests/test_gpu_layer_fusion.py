@@ -19,6 +19,7 @@ CASES = [
     (8, 6, 2, (16, 16), 1, 9, "bfloat16"),      # hparams depth: blocks 5..7 take the conditioning projection computed ahead
     (5, 6, 2, (8, 12), 3, 139, "bfloat16"),     # block 0: 80 row-tile pairs -> the 4-CTA cluster variant (multicast weights), last pair half dummy
     (5, 6, 2, (8, 12), 1, 393, "float16"),      # block 0: 74 pairs = 37 cluster units (odd)
+    (8, 6, 2, (16, 16), 1, 5168, "bfloat16"),   # the C4 shape: block 5 (conditioning projection computed ahead) has 81 row-tile pairs, several per CTA pair
     (2, 2, 3, (2, 2), 2, 300, "bfloat16"),      # 3 layers: the middle one (residual AND running skip) stays on the two-launch path
     (2, 2, 1, (2, 2), 2, 200, "bfloat16"),      # 1 layer: skip only, nothing staged in
 ]

@@ -875,6 +875,15 @@ static bool tail_fusion_enabled() {
   }
   return v == 1;
 }
+// smallest launch (in 256-row tile pairs) that takes the fused layer kernel; FWN_FUSE_MIN_PAIRS overrides (A/B timing)
+static int64_t layer_fusion_min_pairs() {
+  static int64_t v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_FUSE_MIN_PAIRS");
+    v = e ? atoll(e) : 2 * (num_sms() / 2);
+  }
+  return v;
+}
 static bool fp32_front_on_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -969,7 +978,7 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     // G0, G1, R, K of its rows in sequence) loses to two launches that spread the column tiles over twice as many SMs
     // (C1, 1 s / batch 1: 4.42 ms fused vs 3.62 ms per pass)
     const int64_t row_pairs = ((int64_t)B * ((Ti + 127) / 128) + 1) / 2;
-    const bool fuse = m->fuse_layer < 0 ? (layer_fusion_enabled() && row_pairs >= 2 * (num_sms() / 2)) : m->fuse_layer != 0;
+    const bool fuse = m->fuse_layer < 0 ? (layer_fusion_enabled() && row_pairs >= layer_fusion_min_pairs()) : m->fuse_layer != 0;
     if (bf16 && fuse && tc_layer_supported(m, g, r)) {
       // gate GEMM -> tanh*sigmoid -> res|skip 1x1 in one launch: o stays in shared memory (layer_tc.cu)
       prof_begin(m, PROF_GATE, gate_flop + rs_flop, st);
