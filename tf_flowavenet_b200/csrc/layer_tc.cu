@@ -11,13 +11,16 @@
 // CTA pair (cta_group::2, M = 256 rows across the two SMs), per pair of row tiles a fixed program of accumulator "ops", each
 // N = 256 wide, alternating between the two 256-column halves of TMEM:
 //     G0 (gate columns 0..255 -> o channels 0..127), G1 (gate columns 256..511 -> o channels 128..255), [R (residual)], K (skip)
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warps 2..17 two epilogue groups of 8 warps; group g drains
-// TMEM half g, i.e. every other op.  The MMA warp runs ahead as far as TMEM and the o tile allow: the epilogue of G0 overlaps the
-// MMAs of G1, R's first two K chunks (o channels 0..127) are issued before G1's epilogue has finished, the epilogue of R overlaps the
-// MMAs of K, and both overlap the next tile's G0.
+// software-pipelined by one gate half so the 1x1 MMAs never wait for a gate epilogue:
+//     G0(0) G1(0) | G0(1) [R(0)] K(0) G1(1) | G0(2) [R(1)] K(1) G1(2) | ... | [R(n-1)] K(n-1)
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warps 2..17 epilogue.  All 16 epilogue warps work on every
+// op in program order (thread = one row x 64 accumulator columns, one tcgen05.wait::ld) and hand the TMEM half back to the MMA warp
+// BEFORE the arithmetic.  G0(j+1)'s half of the o tile is still the A operand of R(j) / K(j), which are issued right after it: its
+// store is deferred (16 registers) into the next op's epilogue, after that op's accumulator has been fetched and K(j) has completed.
 // Shared memory (227 KB): 3 pipeline stages x (16 KB A + 16 KB weight half-box) | o tile 64 KB | staging tile 64 KB | gate bias.
-// The staging tile carries the in-place epilogue I/O of the 1x1 ops: TMA loads h_in (or the running skip sum) ahead of time, the
-// residual group updates it in place and TMA-stores h_out, then the skip group reuses it for the skip tile.
+// The 1x1 ops pack two weight K chunks into one stage.  The staging tile carries their in-place epilogue I/O: TMA loads h_in (or the
+// running skip sum) one gate half ahead, the residual op updates each warp's 32 x 64 region in place and TMA-stores h_out, then the
+// skip op reuses the region for the skip tile.  Measurements, timelines and the rejected variants: profiles/r2_ncu_fused.md.
 #include <cuda.h>
 #include <stdio.h>
 
@@ -68,15 +71,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   } while (!ok);
 }
 
-// 2-SM TMA load multicast to the CTAs of `cta_mask`: the box lands at the same offset in each of them and the bytes complete on the
-// barrier at this offset in the LEADER (even CTA) of each destination CTA's pair
-__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem)),
-      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 // umma_chunk_commit<true> / umma_commit_elect<true> (tc_ptx.cuh) with an explicit CTA mask for the commit's arrive
 __device__ __forceinline__ void umma_chunk_commit_mask(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
                                                        uint32_t ksteps, uint32_t bar, uint16_t mask) {
@@ -167,10 +161,6 @@ constexpr int L_TRACE_TILES = 8, L_TRACE_K = 8, L_TRACE_T0 = 30;
     }                                                                                                          \
   } while (0)
 
-// CL = CTAs per cluster: 2 = one CTA pair; 4 = two pairs working on neighbouring row-tile pairs in lock step, the weight half-boxes
-// fetched once (by the first pair) and TMA-multicast into both pairs' shared memory -- the weights are the larger half of the
-// kernel's L2->SM traffic, which (not the tensor pipe) bounds it.
-template <int CL>
 __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_constant__ LayerArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage_base = smem;
@@ -183,21 +173,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;         // [2] leader: 16 warps x 2 CTAs hold the half's accumulators in registers
   uint64_t* o_full = tmem_empty + 2;            // [2] leader: o channels [0,128) / [128,256) of both CTAs written
   uint64_t* stg_full = o_full + 2;              // staging tile pre-loaded (TMA)
-  uint64_t* stg_rdone = stg_full + 1;           // (unused)
-  uint64_t* stg_empty = stg_rdone + 1;          // the skip op's stores (16 warps) have read the staging tile
+  uint64_t* stg_empty = stg_full + 1;          // the skip op's stores (16 warps) have read the staging tile
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank4 = (int)cluster_ctarank();
-  const int rank = rank4 & 1, pr = rank4 >> 1;      // role inside the pair / pair inside the cluster
-  const uint32_t lead_cta = (uint32_t)(rank4 & ~1); // cluster rank of this pair's leader
+  const int rank = (int)cluster_ctarank();
+  const uint32_t lead_cta = 0;                      // cluster rank of the pair's leader
   const bool leader = rank == 0;
-  constexpr int PPC = CL / 2;                       // pairs per cluster
-  const uint16_t all_mask = (uint16_t)((1u << CL) - 1), pair_mask = (uint16_t)(3u << (2 * pr));
+  const uint16_t all_mask = 3, pair_mask = 3;       // commit arrives on both CTAs of the pair
   const int num_m_tiles = a.B * a.tiles_per_utt;
   const int n_pairs = (num_m_tiles + 1) / 2;
-  const int cl = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
-  const int n_units = (n_pairs + PPC - 1) / PPC;    // row-tile pairs are dealt to clusters PPC at a time
+  const int cl = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+  const int n_units = n_pairs;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -209,7 +196,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
     prefetch_tmap(&a.mapWr);
     for (int i = 0; i < L_STAGES; ++i) {
       mbar_init(full_bar + i, 1);
-      mbar_init(empty_bar + i, PPC);   // one commit per pair of the cluster
+      mbar_init(empty_bar + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
@@ -217,7 +204,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
       mbar_init(o_full + i, 32);
     }
     mbar_init(stg_full, 1);
-    mbar_init(stg_rdone, 16);
     mbar_init(stg_empty, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -244,7 +230,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
       uint32_t phase = 0;
       pdl_wait();
       auto coords = [&](int it, int& ub, int& t0) {
-        const int m_tile = 2 * ((cl + it * ncl) * PPC + pr) + rank;
+        const int m_tile = 2 * (cl + it * ncl) + rank;
         ub = m_tile / a.tiles_per_utt;
         t0 = (m_tile - ub * a.tiles_per_utt) * BM;
       };
@@ -275,8 +261,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
               const bool skip_a = (a.dbg & 8) && kind == OP_G1;   // diagnostics: how much of the time is the activation traffic?
               if (leader) mbar_expect_tx(full_bar + stage, skip_a ? 2 * A_BYTES : 2 * L_STAGE_BYTES);   // both CTAs' loads complete on the leader's barrier
               if (!skip_a) tma_load_3d_2sm(sa, &a.mapA[s], full_bar + stage, ch * BK, t0 + a.shift[s], ub);
-              if (CL == 2) tma_load_2d_2sm(sa + A_BYTES, &a.mapWg, full_bar + stage, a.wk0[s] + ch * BK, kind * 256 + rank * 128);
-              else if (pr == 0) tma_load_2d_2sm_mc(sa + A_BYTES, &a.mapWg, full_bar + stage, a.wk0[s] + ch * BK, kind * 256 + rank * 128, (uint16_t)(5u << rank));
+              tma_load_2d_2sm(sa + A_BYTES, &a.mapWg, full_bar + stage, a.wk0[s] + ch * BK, kind * 256 + rank * 128);
               if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
               if (pf && !(a.dbg & 16)) tma_prefetch_3d(&a.mapA[s], ch * BK, t02 + a.shift[s], ub2);
               // the 1x1 ops of the previous tile follow this gate half: their staging tile is fetched now, one sub-tile per chunk
@@ -292,13 +277,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * L_STAGE_BYTES;
             if (leader) mbar_expect_tx(full_bar + stage, 2 * L_STAGE_BYTES);
-            if (CL == 2) {
-              tma_load_2d_2sm(sa, &a.mapWr, full_bar + stage, kc * BK, n0);
-              tma_load_2d_2sm(sa + A_BYTES, &a.mapWr, full_bar + stage, (kc + 1) * BK, n0);
-            } else if (pr == 0) {
-              tma_load_2d_2sm_mc(sa, &a.mapWr, full_bar + stage, kc * BK, n0, (uint16_t)(5u << rank));
-              tma_load_2d_2sm_mc(sa + A_BYTES, &a.mapWr, full_bar + stage, (kc + 1) * BK, n0, (uint16_t)(5u << rank));
-            }
+            tma_load_2d_2sm(sa, &a.mapWr, full_bar + stage, kc * BK, n0);
+            tma_load_2d_2sm(sa + A_BYTES, &a.mapWr, full_bar + stage, (kc + 1) * BK, n0);
             if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -375,7 +355,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
     int held_gk = -1;                             // op number of the K op the deferred store waits for, -1 = nothing held
     pdl_wait();
     for_each_op(n_my, a.has_res != 0, [&](int it, int kind, int gop) {
-      const int m_tile = 2 * ((cl + it * ncl) * PPC + pr) + rank;
+      const int m_tile = 2 * (cl + it * ncl) + rank;
       const int ub = m_tile / a.tiles_per_utt;
       const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
       const int t = t0 + r;
@@ -559,40 +539,14 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
     FWN_CUDA(cudaMemsetAsync(trace_buf, 0, (L_TRACE_TILES * 4 * L_TRACE_K + L_TRACE_TILES) * sizeof(long long), st));
     a.trace = trace_buf;
   }
-  // FWN_LAYER_CLUSTER = 2 (default: one CTA pair per cluster) | 4 (EXPERIMENTAL: two pairs sharing multicast weight loads; parity-clean
-  // on small launches, no faster with the epilogue traffic switched off (26.9 vs 28.6 ms per C3 pass) and it stalls on full-size
-  // launches -- kept for diagnostics only)
-  static int cl_size = 0, max_cl4 = 0;
-  if (!cl_size) {
-    const char* e = getenv("FWN_LAYER_CLUSTER");
-    cl_size = (e && e[0] == '4') ? 4 : 2;
-    FWN_CUDA(cudaFuncSetAttribute(layer_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
-    FWN_CUDA(cudaFuncSetAttribute(layer_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
-    if (cl_size == 4) {   // how many 4-CTA clusters fit at once (GPCs whose SM count is not a multiple of 4 leave SMs over)
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3((unsigned)(num_sms() / 4 * 4));
-      q.blockDim = dim3(L_THREADS);
-      q.dynamicSmemBytes = L_SMEM;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = 4;
-      qa[0].val.clusterDim.y = 1;
-      qa[0].val.clusterDim.z = 1;
-      q.attrs = qa;
-      q.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&max_cl4, layer_kernel<4>, &q) != cudaSuccess || max_cl4 <= 0) {
-        cudaGetLastError();
-        max_cl4 = num_sms() / 4;
-      }
-      if (getenv("FWN_TRACE")) fprintf(stderr, "layer_kernel<4>: %d clusters of 4 CTAs resident at once (%d SMs)\n", max_cl4, num_sms());
-    }
+  static bool configured = false;
+  if (!configured) {
+    FWN_CUDA(cudaFuncSetAttribute(layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
+    configured = true;
   }
   const int num_m = a.B * a.tiles_per_utt;
   const int pairs = (num_m + 1) / 2;
-  // small launches keep the pair kernel: a 4-CTA cluster deals tiles 512 rows at a time
-  const int csz = (cl_size == 4 && pairs >= 2 * max_cl4) ? 4 : 2;
-  const int units = csz == 4 ? (pairs + 1) / 2 : pairs;
-  const int grid = csz * std::min(units, csz == 4 ? max_cl4 : num_sms() / 2);
+  const int grid = 2 * std::min(pairs, num_sms() / 2);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(L_THREADS);
@@ -601,7 +555,7 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
   cudaLaunchAttribute attr[2];
   int na = 0;
   attr[na].id = cudaLaunchAttributeClusterDimension;
-  attr[na].val.clusterDim.x = csz;
+  attr[na].val.clusterDim.x = 2;
   attr[na].val.clusterDim.y = 1;
   attr[na].val.clusterDim.z = 1;
   ++na;
@@ -612,8 +566,7 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (csz == 4) FWN_CUDA(cudaLaunchKernelEx(&cfg, layer_kernel<4>, a));
-  else FWN_CUDA(cudaLaunchKernelEx(&cfg, layer_kernel<2>, a));
+  FWN_CUDA(cudaLaunchKernelEx(&cfg, layer_kernel, a));
   FWN_LAUNCH_CHECK();
   if (tracing) {   // diagnostics only (run with FWN_GRAPH=0): timeline of the first tiles of cluster 0, cycles relative to the first event
     long long h[L_TRACE_TILES * 4 * L_TRACE_K + L_TRACE_TILES];
