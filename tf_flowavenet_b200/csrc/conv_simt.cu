@@ -317,6 +317,10 @@ __global__ void __launch_bounds__(256, 2) front_direct_kernel(const FrontArgs a,
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + 4));
     bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
   }
+  // programmatic dependent launch: the weights above do not depend on the previous kernel of the chain (the tail of the previous flow),
+  // everything below does (ActNorm parameters during the data-dependent init pass, x always)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // physical offset of logical pass-through channel q inside a row of X, and its ActNorm (identity in the reverse direction)
   if (threadIdx.x < a.Cx) {
     const int o = threadIdx.x, l = __ldg(a.off2log + o);
@@ -384,13 +388,23 @@ int front_direct(const FrontArgs& a, bool fp16, cudaStream_t st) {
   FWN_CHECK(front_direct_supported(a), "front_direct: needs F = 256, nq in {1, 2, 4} and |shift| <= 32");
   int lo = 0, hi = 0;
   for (int k = 0; k < 3; ++k) { lo = std::min(lo, a.shift[k]); hi = std::max(hi, a.shift[k]); }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {   // see the kernel: its weight loads overlap the tail of the previous kernel of the chain
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
 #define FWN_FD(NQ, ROWS)                                                                                             \
   {                                                                                                                  \
     const int tiles_per_utt = (a.Ti + ROWS - 1) / ROWS;                                                              \
     const int n_tiles = a.B * tiles_per_utt;                                                                         \
-    const int grid = std::min(n_tiles, num_sms() * 2);                                                               \
-    if (fp16) front_direct_kernel<NQ, __half, ROWS><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);        \
-    else front_direct_kernel<NQ, __nv_bfloat16, ROWS><<<grid, 256, 0, st>>>(a, lo, hi, tiles_per_utt, n_tiles);      \
+    cfg.gridDim = dim3((unsigned)std::min(n_tiles, num_sms() * 2));                                                  \
+    if (fp16) FWN_CUDA(cudaLaunchKernelEx(&cfg, front_direct_kernel<NQ, __half, ROWS>, a, lo, hi, tiles_per_utt, n_tiles));        \
+    else FWN_CUDA(cudaLaunchKernelEx(&cfg, front_direct_kernel<NQ, __nv_bfloat16, ROWS>, a, lo, hi, tiles_per_utt, n_tiles));      \
   }
   // big tiles only when they still give every SM several tiles; short inputs keep 64-row tiles (more blocks in flight)
   bool big = (int64_t)a.B * a.Ti >= (int64_t)256 * 4 * num_sms();
