@@ -138,3 +138,28 @@ def test_bf16_training_trajectory():
     print("loss trajectory fp32 %s | bf16 %s" % (["%.5f" % v for v in l32], ["%.5f" % v for v in l16]))
     assert l16[-1] < l16[0]
     assert max(abs(a - b) for a, b in zip(l32, l16)) < 2e-2
+
+
+def test_fp32_passes_after_bf16_steps_use_fresh_operands():
+    """The bf16 optimizer step refreshes only plane 0 of the split engine's three operand planes (it reads nothing else); the fp32
+    passes of the same handle (model.py:317-396 on the trained variables) must see all three refreshed.  After three bf16 steps the fp32
+    forward equals the float64 oracle on the CURRENT variables (1e-4), and an explicit full re-pack changes nothing."""
+    import tf_flowavenet_b200.train as T
+    from tf_flowavenet_b200 import _lib
+    hp, params, fx = load("g1_b2f2l2")
+    x, c = torch.from_numpy(fx["x"]).float().cuda(), torch.from_numpy(fx["c"]).float().cuda()
+    net = make_model(hp, params)
+    tr = T.Trainer(net, compute_dtype="bfloat16")
+    for _ in range(3):
+        tr.train_step(x, c)
+    lp, ld, z = net.forward(x, c, return_z=True)
+    cur = {k: v.detach().cpu() for k, v in net.variables().items()}
+    wlp, wld, wz = O.forward(cur, hp, x.cpu(), c.cpu(), torch.float64)
+    err = float((z.cpu().double() - wz).abs().max() / wz.abs().max())
+    print("fp32 forward after 3 bf16 steps: z rel-to-max %.2e, log_p %.6f vs %.6f" % (err, float(lp), float(wlp)))
+    assert err < 1e-4 and abs(float(lp) - float(wlp)) < 1e-4 * max(1.0, abs(float(wlp)))
+    _lib.check(_lib.lib().fwn_repack(net._h, _lib.stream_ptr()))
+    lp2, ld2, z2 = net.forward(x, c, return_z=True)
+    assert torch.equal(z, z2)
+    # and the fp32 training mode on the same handle after bf16 steps: gradients of the current variables against the oracle
+    tr.train_step(x, c)

@@ -1149,6 +1149,7 @@ int model_forward(Model* m, const float* x, const float* c, const int32_t* g, in
   Workspace w;
   if (check_pass_args(m, x, c, g, B, T, ws, ws_bytes, &w)) return 1;
   if (prepare_engine(m, w, B, T, st)) return 1;
+  if (train_ensure_full_planes(m, st)) return 1;   // after bf16 optimizer steps planes 1, 2 of the fp32 operand planes are stale
   // the flow variable lives in the workspace for the whole pass (fixed address -> the flow chain can be a CUDA graph)
   float* X = w.x;
   FWN_CUDA(cudaMemcpyAsync(X, x, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
@@ -1186,6 +1187,7 @@ int model_reverse(Model* m, const float* z, const float* c, const int32_t* g, in
   FWN_CHECK(m->rev_ok, "fused reverse needs an even n_flow: with odd n_flow the reference's reverse is not the inverse of forward "
                        "(change_order parity, model.py:199,359) -- use the per-op Block/Flow API for that case");
   if (prepare_engine(m, w, B, T, st)) return 1;
+  if (train_ensure_full_planes(m, st)) return 1;
   float* X = w.x;
   FWN_CUDA(cudaMemcpyAsync(X, z, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
   if (run_upsample(m, w, c, B, T, st)) return 1;

@@ -97,6 +97,7 @@ struct Model {
   bool train_exact_fwd = false, force_simt = false;
   // training compute dtype: false = fp32-accurate (split engine), true = bf16 operands / tape on the tcgen05 engine (train16.cu)
   bool train_bf16 = false;
+  bool planes_partial = false;   // planes 1, 2 of the split engine's operand planes are stale (bf16 optimizer steps refresh plane 0 only)
   // mixed inference passes: 1 = fused ResBlock-layer kernel (layer_tc.cu), 0 = gate GEMM + res|skip GEMM as two launches, -1 = FWN_FUSE_LAYER / default
   int fuse_layer = -1;
   bool packed = false, rev_ok = false;
@@ -154,6 +155,7 @@ int run_gemm(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowP
 void engine_free(Model* m);
 // fused ResBlock layer on the tcgen05 engine (gemm_tc.cu / layer_tc.cu): gate GEMM `g` + res|skip 1x1 `r` of layer `layer`
 bool tc_layer_supported(const Model* m, const GemmArgs& g, const GemmArgs& r);
+int train_ensure_full_planes(Model* m, cudaStream_t st);   // train.cu
 int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st);
 // fused WaveNet tail (gemm_tc.cu / tail_tc.cu): final 1x1 `f` + zero conv / affine coupling `z`
 bool tc_tail_supported(const Model* m, const GemmArgs& f, const GemmArgs& z);

@@ -206,14 +206,15 @@ int train_enable(Model* m, cudaStream_t st) {
 int train_after_prepack(Model* m) { return m->keep_map ? train_build(m) : 0; }
 
 // raw variables -> every derived operand, on the device (what fwn_prepack does on the host)
-int train_repack(Model* m, cudaStream_t st) {
+int train_repack(Model* m, cudaStream_t st, bool plane0_only) {
   TrainState* t = m->train;
   FWN_CHECK(t, "training not enabled: call fwn_train_enable first");
   const fwn_config& c = m->cfg;
   m->launches += 4 + 1 * c.n_upsample;
   if (fold_forward(m->raw, t->what, t->d_folds, t->d_fwork, t->n_fwork, m->raw_floats, st)) return 1;
   if (gather_pack(t->what, t->wmap, reinterpret_cast<float*>(m->pack), m->wall_floats, st)) return 1;
-  if (make_planes(t->d_pdesc, t->d_pwork, t->n_pwork, st)) return 1;
+  if (make_planes(t->d_pdesc, t->d_pwork, t->n_pwork, plane0_only ? 1 : 3, st)) return 1;
+  m->planes_partial = plane0_only;
   if (actnorm_pack(t->d_an, (int)m->flows.size(), m->d_an_logdet, st)) return 1;
   for (int i = 0; i < c.n_upsample; ++i) {
     const std::string n = i == 0 ? "conv2d_transpose" : "conv2d_transpose_" + std::to_string(i);
@@ -223,6 +224,14 @@ int train_repack(Model* m, cudaStream_t st) {
     if (upsample_weight_norm(v, g, m->up_w[i], c.upsample_scales[i], st)) return 1;
     FWN_CUDA(cudaMemcpyAsync(m->up_b[i], b, sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  return 0;
+}
+int train_ensure_full_planes(Model* m, cudaStream_t st) {
+  if (!m->planes_partial || !m->train) return 0;
+  TrainState* t = m->train;
+  m->launches += 1;
+  if (make_planes(t->d_pdesc, t->d_pwork, t->n_pwork, 3, st)) return 1;
+  m->planes_partial = false;
   return 0;
 }
 
@@ -596,6 +605,7 @@ int train_loss_and_grads(Model* m, const float* x, const float* cmel, const int3
   FWN_CHECK(!(m->cfg.gin_channels > 0 && gspk == nullptr), "g is None");
   FWN_CHECK(grad_floats >= train_grad_floats(m), "gradient buffer too small: need %lld floats", (long long)train_grad_floats(m));
   if (m->train_bf16) return train16_loss_and_grads(m, x, cmel, gspk, B, T, logp_out, logdet_out, grads, grad_floats, ws, ws_bytes, st);
+  if (train_ensure_full_planes(m, st)) return 1;
   TrainWs w;
   if (train_plan(m, B, T, &w, (char*)ws)) return 1;
   FWN_CHECK(ws && ws_bytes >= (int64_t)w.bytes, "workspace too small: need %lld bytes, got %lld", (long long)w.bytes, (long long)ws_bytes);
@@ -711,7 +721,7 @@ int train_apply(Model* m, const float* grads, float lr, float beta1, float beta2
   m->launches += 3;
   if (grad_global_norm(grads, m->raw_floats, t->scratch, t->norm, st)) return 1;
   if (adam_update(m->raw, t->adam_m, t->adam_v, grads, t->norm, clip_norm, lr, beta1, beta2, eps, step, m->raw_floats, st)) return 1;
-  return train_repack(m, st);
+  return train_repack(m, st, m->train_bf16);   // the bf16 step reads plane 0 of the operand planes only
 }
 
 }  // namespace fwn

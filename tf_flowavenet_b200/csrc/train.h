@@ -94,7 +94,7 @@ int fold_forward(const float* raw, float* what, const FoldDesc* descs, const Fol
 int fold_backward(const float* raw, float* G, const FoldDesc* descs, const FoldWork* work, int nwork, int64_t raw_floats, cudaStream_t st);
 int gather_pack(const float* what, const int32_t* map, float* P, int64_t n, cudaStream_t st);
 int scatter_grad(const float* gP, const int32_t* map, float* G, int64_t n, cudaStream_t st);
-int make_planes(const PlaneDesc* descs, const PlaneWork* work, int nwork, cudaStream_t st);
+int make_planes(const PlaneDesc* descs, const PlaneWork* work, int nwork, int nplanes, cudaStream_t st);
 int actnorm_pack(const ActnormDesc* descs, int nflows, double* an_logdet, cudaStream_t st);
 int wgrad(const WgradArgs& a, cudaStream_t st);
 int colsum(const float* dY0, int64_t ld0, int n0cols, const float* dY1, int64_t ld1, int N, int64_t rows, float* out, cudaStream_t st);
@@ -154,7 +154,10 @@ int train_bucket_range(const Model* m, int k, int64_t* off, int64_t* count);
 int train_bucket_wait(const Model* m, int k, cudaStream_t consumer);
 int train_grad_norm(Model* m, const float* grads, float* norm_out, cudaStream_t st);
 int train_apply(Model* m, const float* grads, float lr, float beta1, float beta2, float eps, float clip_norm, int64_t step, cudaStream_t st);
-int train_repack(Model* m, cudaStream_t st);
+int train_repack(Model* m, cudaStream_t st, bool plane0_only = false);
+// the optimizer step of the bf16 mode refreshes plane 0 of the operand planes only; anything that reads all three (fp32 passes, the
+// fp32 training mode) calls this first
+int train_ensure_full_planes(Model* m, cudaStream_t st);
 int train_state_copy(Model* m, int which, float* dst, const float* src, int64_t numel, cudaStream_t st);
 
 }  // namespace fwn

@@ -189,7 +189,7 @@ int scatter_grad(const float* gP, const int32_t* map, float* G, int64_t n, cudaS
 }
 
 // ---------------------------------------------------------------- fp32 operand -> bf16x3 planes [3][Npad][Kpad]
-__global__ void make_planes_kernel(const PlaneDesc* __restrict__ descs, const PlaneWork* __restrict__ work) {
+__global__ void make_planes_kernel(const PlaneDesc* __restrict__ descs, const PlaneWork* __restrict__ work, int nplanes) {
   __shared__ float tile[32][33];
   const PlaneWork wk = work[blockIdx.x];
   const PlaneDesc d = descs[wk.desc];
@@ -219,12 +219,14 @@ __global__ void make_planes_kernel(const PlaneDesc* __restrict__ descs, const Pl
     const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
     const size_t i = (size_t)n * d.Kpad + d.k0 + k;
     d.dst[i] = h1;
-    d.dst[plane + i] = h2;
-    d.dst[2 * plane + i] = h3;
+    if (nplanes == 3) {   // the bf16 training mode reads plane 0 only
+      d.dst[plane + i] = h2;
+      d.dst[2 * plane + i] = h3;
+    }
   }
 }
-int make_planes(const PlaneDesc* descs, const PlaneWork* work, int nwork, cudaStream_t st) {
-  if (nwork) make_planes_kernel<<<nwork, 256, 0, st>>>(descs, work);
+int make_planes(const PlaneDesc* descs, const PlaneWork* work, int nwork, int nplanes, cudaStream_t st) {
+  if (nwork) make_planes_kernel<<<nwork, 256, 0, st>>>(descs, work, nplanes);
   FWN_LAUNCH_CHECK();
   return 0;
 }
