@@ -280,7 +280,9 @@ __global__ void affine_kernel(const float* __restrict__ x, const float* __restri
   }
 }
 // 128-bit variant of the affine coupling.  MODE 0: (C/2) % 4 == 0 (one float4 of the transformed half + the matching
-// pass-through float4 per thread); MODE 2: C == 2 (two rows per float4); MODE 4: C == 4 (one row per float4).
+// pass-through float4 per thread); MODE 2: C == 2 (two rows per float4); MODE 4: C == 4 (one row per float4); MODE 8: C == 8 (a row = two
+// float4: consecutive lanes take consecutive float4 of x / net / y -- fully coalesced -- and the odd lane, which owns the transformed half,
+// gets log_s from its even neighbour's net float4 by shuffle; the generic MODE 0 mapping makes every lane stride by 32 bytes there).
 template <bool REV, int MODE>
 __global__ void affine_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ net, float4* __restrict__ y, double* __restrict__ acc,
                                   int64_t nwork, int C) {
@@ -298,6 +300,17 @@ __global__ void affine_vec_kernel(const float4* __restrict__ x, const float4* __
     } else if (MODE == 4) {  // x = (a0 a1 b0 b1), net = (ls0 ls1 t0 t1)
       const float4 v = __ldg(x + i), w = __ldg(net + i);
       y[i] = make_float4(v.x, v.y, tr(v.z, w.x, w.z), tr(v.w, w.y, w.w));
+    } else if (MODE == 8) {  // float4 2r = pass-through half of row r, 2r+1 = transformed half; net float4 2r = log_s, 2r+1 = t
+      // (the grid-stride keeps whole warps inside or outside the loop: nwork and the stride are multiples of 32)
+      float4 v = __ldg(x + i);
+      const float4 w = __ldg(net + i);
+      float4 l;
+      l.x = __shfl_up_sync(0xffffffffu, w.x, 1);
+      l.y = __shfl_up_sync(0xffffffffu, w.y, 1);
+      l.z = __shfl_up_sync(0xffffffffu, w.z, 1);
+      l.w = __shfl_up_sync(0xffffffffu, w.w, 1);
+      if (i & 1) v = make_float4(tr(v.x, l.x, w.x), tr(v.y, l.y, w.y), tr(v.z, l.z, w.z), tr(v.w, l.w, w.w));
+      y[i] = v;
     } else {
       const int hq = C / 8, q = C / 4;  // float4 per half row / per row
       const int64_t row = i / hq;
@@ -322,16 +335,17 @@ int affine(const float* x, const float* net, float* y, float* logdet_out, int64_
   if (n == 0) return 0;
   int grid = ew_grid(n, 256);
   if (scratch) FWN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
-  const int mode = C == 2 ? 2 : (C == 4 ? 4 : ((C / 2) % 4 == 0 ? 0 : -1));
+  int mode = C == 2 ? 2 : (C == 4 ? 4 : ((C / 2) % 4 == 0 ? 0 : -1));
+  if (C == 8 && (n / 4) % 32 == 0) mode = 8;   // whole warps only (the shuffle needs both lanes of a row)
   const bool vec = affine_ && mode >= 0 && n % 4 == 0 && aligned16(x, y) && aligned16(net, net);
   if (vec) {
-    const int64_t nwork = mode == 0 ? rows * (C / 8) : n / 4;
+    const int64_t nwork = mode == 0 ? rows * (C / 8) : n / 4;   // float4 of the transformed half (mode 0) or all float4
     const int g2 = ew_grid(nwork, 256);
     const float4 *x4 = (const float4*)x, *n4 = (const float4*)net;
     float4* y4 = (float4*)y;
 #define FWN_AFF(R, M) affine_vec_kernel<R, M><<<g2, 256, 0, st>>>(x4, n4, y4, R ? nullptr : scratch, nwork, C)
-    if (rev) { if (mode == 2) FWN_AFF(true, 2); else if (mode == 4) FWN_AFF(true, 4); else FWN_AFF(true, 0); }
-    else { if (mode == 2) FWN_AFF(false, 2); else if (mode == 4) FWN_AFF(false, 4); else FWN_AFF(false, 0); }
+    if (rev) { if (mode == 2) FWN_AFF(true, 2); else if (mode == 4) FWN_AFF(true, 4); else if (mode == 8) FWN_AFF(true, 8); else FWN_AFF(true, 0); }
+    else { if (mode == 2) FWN_AFF(false, 2); else if (mode == 4) FWN_AFF(false, 4); else if (mode == 8) FWN_AFF(false, 8); else FWN_AFF(false, 0); }
 #undef FWN_AFF
   } else if (affine_) {
     if (rev) affine_kernel<true, true><<<grid, 256, 0, st>>>(x, net, y, nullptr, rows, C);

@@ -12,23 +12,39 @@ if os.path.exists(p):
     PEAK = json.load(open(p))["hbm_gbs"]
 
 
-def timeit(fn, iters=20):
+from bench import ClockSampler  # nvidia-smi clocks / throttle reasons sampled DURING each op's timed region
+
+LAST_CLOCKS = None
+
+
+def timeit(fn, iters=200):
+    """ms per call; >= 200 iterations so the nvidia-smi sampler (100 ms period) sees the op under load."""
+    global LAST_CLOCKS
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    cs = ClockSampler(0)
+    cs.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    ms = e0.elapsed_time(e1) / iters
+    if ms * iters < 250:   # keep the op running long enough for a few clock samples
+        extra = int(250 / max(ms, 1e-3))
+        for _ in range(extra):
+            fn()
+        torch.cuda.synchronize()
+    LAST_CLOCKS = cs.stop()
+    return ms
 
 
 def report(name, ms, nbytes, shape):
     gbs = nbytes / ms / 1e6
     print(json.dumps({"op": name, "shape": shape, "ms": round(ms, 4), "algorithmic_GB": round(nbytes / 1e9, 3), "GBps": round(gbs, 1),
-                      "frac_of_measured_hbm_peak": round(gbs / PEAK, 3)}))
+                      "frac_of_measured_hbm_peak": round(gbs / PEAK, 3), "clocks": LAST_CLOCKS}), flush=True)
 
 
 def main():
