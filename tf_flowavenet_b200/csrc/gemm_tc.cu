@@ -970,6 +970,8 @@ int tc_run(Model* m, const GemmArgs& g, EpiKind kind, int gemm_id, const FlowPac
   return tc::tc_launch(a, kind, bn, ws, st);
 }
 
+int tc_map_3d(CUtensorMap* out, const void* base, int C, int Ti, int B, int64_t ld, int box_c, int box_rows, bool fp16);   // below (cached)
+
 // Fused ResBlock layer (layer_tc.cu): the gate GEMM `g` and the res|skip 1x1 `r` of one layer in one launch; o never leaves the SM.
 // Supported: the CTA-pair gate path, F = 256, and a 1x1 whose staged epilogue input is single (first layer: h_in; last layer: the
 // running skip sum) -- a middle layer of a deeper WaveNet (residual AND running skip) takes the two-launch path.
@@ -979,11 +981,13 @@ bool tc_layer_supported(const Model* m, const GemmArgs& g, const GemmArgs& r) {
   if (r.e.has_res && r.e.in1) return false;
   return true;
 }
-int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st) {
+// f, z (optional, last layer only): the final 1x1 and the zero conv + affine coupling are folded into the same launch (the tail ops of
+// layer_tc.cu); the caller has checked tc_tail_supported and that the layer's staged input is the running skip sum.
+int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st, const GemmArgs* fin, const GemmArgs* zero) {
   TcPlan* p = m->tc;
   FWN_CHECK(p, "tcgen05 engine not prepared");
-  const size_t f = (size_t)(&fp - m->flows.data());
-  const int block = (int)(f / m->cfg.n_flow);
+  const size_t fi_ = (size_t)(&fp - m->flows.data());
+  const int block = (int)(fi_ / m->cfg.n_flow);
   tc::LayerArgs a;
   memset(&a, 0, sizeof(a));
   a.nseg = g.nseg;
@@ -997,8 +1001,8 @@ int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, cons
     a.last_ksteps[s] = (K16 - (a.nchunk[s] - 1) * tc::BK) / tc::UMMA_K;
     a.wk0[s] = g.seg[s].koff;
   }
-  a.mapWg = p->wmap[f * GEMM_IDS + GEMM_GATE0 + layer];
-  a.mapWr = p->wmap[f * GEMM_IDS + GEMM_RS0 + layer];
+  a.mapWg = p->wmap[fi_ * GEMM_IDS + GEMM_GATE0 + layer];
+  a.mapWr = p->wmap[fi_ * GEMM_IDS + GEMM_RS0 + layer];
   auto act_map = [&](const void* ptr, CUtensorMap* dst) -> bool {
     const int ai = ptr ? act_index(p->w, ptr) : -1;
     if (ai < 0) return false;
@@ -1029,6 +1033,19 @@ int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, cons
   a.rs_bias = r.e.bias;
   a.pc = reinterpret_cast<const float*>(g.e.in0);
   a.pc_ld = g.e.ld;
+  if (fin && zero) {
+    FWN_CHECK(!a.has_res && a.has_in, "tc_run_layer: the tail can only follow a last layer with a running skip sum");
+    a.tail = 1;
+    a.mapWf = p->wmap[fi_ * GEMM_IDS + GEMM_FINAL];
+    FWN_CHECK(p->wbn[fi_ * GEMM_IDS + GEMM_FINAL] == 128, "tc_run_layer: final-conv weight map has the wrong box");
+    a.Nz = zero->N;
+    a.NzBox = std::min(p->wbn[fi_ * GEMM_IDS + GEMM_ZERO], (zero->N + 15) / 16 * 16);
+    FWN_CHECK(a.NzBox == 16 || a.NzBox == 32, "tc_run_layer: zero conv too wide (%d)", a.NzBox);
+    const int Npad = (zero->N + 15) / 16 * 16;
+    if (tc_map_3d(&a.mapWz, fp.zero_w, fp.zero_ld, Npad, 0, fp.zero_ld, tc::BK, a.NzBox / 2, a.fp16 != 0)) return 1;
+    a.final_bias = fin->e.bias;
+    a.ez = zero->e;
+  }
   return tc::launch_layer(a, st);
 }
 

@@ -129,19 +129,24 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-enum LOp { OP_G0 = 0, OP_G1 = 1, OP_RES = 2, OP_SKIP = 3 };
+enum LOp { OP_G0 = 0, OP_G1 = 1, OP_RES = 2, OP_SKIP = 3, OP_FIN = 4, OP_ZERO = 5 };
 
-// The op program of one CTA pair over its n row-tile pairs -- see layer_kernel.  f(tile, kind, gop) is called once per op, in order.
+// The op program of one CTA pair over its n row-tile pairs -- see layer_kernel.  f(tile, kind, gop) is called once per op, in order:
+//   layer only:   G0(0) G1(0) | G0(1) [R(0)] K(0) G1(1) | G0(2) [R(1)] K(1) G1(2) | ... | [R(n-1)] K(n-1)
+//   with tail:    G0(0) G1(0) | G0(1) K(0) G1(1) F(0) | G0(2) Z(0) K(1) G1(2) F(1) | ... | Z(n-2) K(n-1) F(n-1) | Z(n-1)
+// (every op that consumes an epilogue's shared-memory tile is issued one gate half after the op that produces it)
 template <typename F>
-__device__ __forceinline__ void for_each_op(int n, bool has_res, F&& f) {
+__device__ __forceinline__ void for_each_op(int n, bool has_res, bool tail, F&& f) {
   int gop = 0;
-  for (int jb = -1; jb < n; ++jb)
-    for (int step = 0; step < 4; ++step) {
+  for (int jb = -1; jb < n + (tail ? 1 : 0); ++jb)
+    for (int step = 0; step < 6; ++step) {
       int it, kind;
       if (step == 0) { if (jb + 1 >= n) continue; it = jb + 1; kind = OP_G0; }
-      else if (step == 1) { if (jb < 0 || !has_res) continue; it = jb; kind = OP_RES; }
-      else if (step == 2) { if (jb < 0) continue; it = jb; kind = OP_SKIP; }
-      else { if (jb + 1 >= n) continue; it = jb + 1; kind = OP_G1; }
+      else if (step == 1) { if (!tail || jb < 1) continue; it = jb - 1; kind = OP_ZERO; }
+      else if (step == 2) { if (jb < 0 || jb >= n || !has_res) continue; it = jb; kind = OP_RES; }
+      else if (step == 3) { if (jb < 0 || jb >= n) continue; it = jb; kind = OP_SKIP; }
+      else if (step == 4) { if (jb + 1 >= n) continue; it = jb + 1; kind = OP_G1; }
+      else { if (!tail || jb < 0 || jb >= n) continue; it = jb; kind = OP_FIN; }
       f(it, kind, gop);
       ++gop;
     }
@@ -152,11 +157,11 @@ constexpr int L_TRACE_TILES = 8, L_TRACE_K = 8, L_TRACE_T0 = 30;
 #define L_TRACE(k)                                                                                             \
   do {                                                                                                         \
     if (a.trace && blockIdx.x == 0 && it >= L_TRACE_T0 && it < L_TRACE_T0 + L_TRACE_TILES && lane == 0) {       \
-      a.trace[((it - L_TRACE_T0) * 4 + kind) * L_TRACE_K + (k)] = clock64();                                   \
+      a.trace[((it - L_TRACE_T0) * 6 + kind) * L_TRACE_K + (k)] = clock64();                                   \
       if ((k) == 1 && kind == OP_G0) {                                                                         \
         unsigned long long gt_;                                                                                \
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                \
-        a.trace[L_TRACE_TILES * 4 * L_TRACE_K + (it - L_TRACE_T0)] = (long long)gt_;                           \
+        a.trace[L_TRACE_TILES * 6 * L_TRACE_K + (it - L_TRACE_T0)] = (long long)gt_;                           \
       }                                                                                                        \
     }                                                                                                          \
   } while (0)
@@ -174,7 +179,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
   uint64_t* o_full = tmem_empty + 2;            // [2] leader: o channels [0,128) / [128,256) of both CTAs written
   uint64_t* stg_full = o_full + 2;              // staging tile pre-loaded (TMA)
   uint64_t* stg_empty = stg_full + 1;          // the skip op's stores (16 warps) have read the staging tile
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_empty + 1);
+  uint64_t* su_full = stg_empty + 1;            // [2] tail, leader: relu(skip) / relu(final) tile of both CTAs written (16 warps x 2)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(su_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -194,6 +200,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
     for (int s = 0; s < a.nseg; ++s) prefetch_tmap(&a.mapA[s]);
     prefetch_tmap(&a.mapWg);
     prefetch_tmap(&a.mapWr);
+    if (a.tail) {
+      prefetch_tmap(&a.mapWf);
+      prefetch_tmap(&a.mapWz);
+    }
     for (int i = 0; i < L_STAGES; ++i) {
       mbar_init(full_bar + i, 1);
       mbar_init(empty_bar + i, 1);
@@ -205,6 +215,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
     }
     mbar_init(stg_full, 1);
     mbar_init(stg_empty, 16);
+    mbar_init(su_full, 32);
+    mbar_init(su_full + 1, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 512; i += L_THREADS) sbias[i] = __ldg(a.gate_bias + i);
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
   // (the 1x1 ops of tile j are issued after the first gate half of tile j+1: by then G1(j)'s epilogue has had a whole gate half to
   // finish the o tile).  Every role walks the same sequence; op number gop uses TMEM half gop & 1.
   const int n_my = (n_units - cl + ncl - 1) / ncl;
-  const int k_after_g0 = a.has_res ? 2 : 1;   // K(j) is this many ops after G0(j+1)
+  const bool tail = a.tail != 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -236,7 +248,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
       };
       // staging tile of tile js (h_in for the residual op / running skip sum of the last layer), one 16 KB sub-tile per call
       auto stage_in = [&](int js, int sub) {
-        if (!a.has_in || (a.dbg & 2)) return;
+        if (!a.has_in || tail || (a.dbg & 2)) return;   // with the tail fused in, the epilogue warps reload the staging tile themselves
         int ub, t0;
         coords(js, ub, t0);
         if (sub == 0) {
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
         }
         tma_load_3d(stg + (size_t)sub * A_BYTES, &a.mapIn, stg_full, sub * 64, t0, ub);
       };
-      for_each_op(n_my, a.has_res != 0, [&](int it, int kind, int gop) {
+      for_each_op(n_my, a.has_res != 0, tail, [&](int it, int kind, int gop) {
         (void)gop;
         int ub, t0;
         coords(it, ub, t0);
@@ -268,17 +280,26 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
               if (kind == OP_G0 && it >= 1 && c < 4) stage_in(it - 1, c);
             }
           }
+        } else if (kind == OP_ZERO) {
+          // zero conv: four K chunks of this CTA's NzBox/2 weight rows, all in one stage
+          const uint32_t zb = (uint32_t)(a.NzBox / 2) * 128u;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = stage_base + (size_t)stage * L_STAGE_BYTES;
+          if (leader) mbar_expect_tx(full_bar + stage, 2u * 4u * zb);
+          for (int kc = 0; kc < 4; ++kc) tma_load_2d_2sm(sa + (size_t)kc * zb, &a.mapWz, full_bar + stage, kc * BK, rank * (a.NzBox / 2));
+          if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
         } else {
-          if (it == n_my - 1 && (kind == OP_RES || !a.has_res))   // last tile: no gate half precedes its 1x1 ops
+          if (it == n_my - 1 && !tail && (kind == OP_RES || (kind == OP_SKIP && !a.has_res)))   // last tile: no gate half precedes its 1x1 ops
             for (int sub = 0; sub < 4; ++sub) stage_in(it, sub);
-          // 1x1 ops: only the weight half-boxes stream; the A operand is the o tile
+          // 1x1 ops (residual / skip on the o tile, final conv on the staging tile): only the weight half-boxes stream
+          const CUtensorMap* wm = kind == OP_FIN ? &a.mapWf : &a.mapWr;
           const int n0 = ((a.has_res && kind == OP_SKIP) ? 256 : 0) + rank * 128;
           for (int kc = 0; kc < 4; kc += 2) {   // two K chunks of weight half-boxes per stage (a stage has room for an A and a B box)
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* sa = stage_base + (size_t)stage * L_STAGE_BYTES;
             if (leader) mbar_expect_tx(full_bar + stage, 2 * L_STAGE_BYTES);
-            tma_load_2d_2sm(sa, &a.mapWr, full_bar + stage, kc * BK, n0);
-            tma_load_2d_2sm(sa + A_BYTES, &a.mapWr, full_bar + stage, (kc + 1) * BK, n0);
+            tma_load_2d_2sm(sa, wm, full_bar + stage, kc * BK, n0);
+            tma_load_2d_2sm(sa + A_BYTES, wm, full_bar + stage, (kc + 1) * BK, n0);
             if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -293,7 +314,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
       const uint64_t desc_hi = make_smem_desc(0);
       int stage = 0;
       uint32_t phase = 0;
-      for_each_op(n_my, a.has_res != 0, [&](int it, int kind, int gop) {
+      for_each_op(n_my, a.has_res != 0, tail, [&](int it, int kind, int gop) {
         const int slot = gop & 1;
         L_TRACE(0);
         mbar_wait(tmem_empty + slot, (((uint32_t)gop >> 1) & 1) ^ 1);
@@ -315,15 +336,36 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
               if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
             }
           }
+        } else if (kind == OP_ZERO) {
+          // zero conv: A = relu(final) in the staging tile (u_full), B = the stage's four small weight boxes, N = NzBox
+          mbar_wait_cluster(su_full + 1, (uint32_t)it & 1);
+          mbar_wait(full_bar + stage, phase);
+          tcgen05_fence_after();
+          const uint32_t idesc_z = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(a.NzBox >> 3) << 17);
+          const uint32_t zb = (uint32_t)(a.NzBox / 2) * 128u, sb0 = stage0 + (uint32_t)stage * L_STAGE_BYTES, st0 = smem_u32(stg);
+          for (int kc = 0; kc < 3; ++kc)
+            umma_chunk_pair(tmem_d, desc_hi | (uint64_t)(((st0 + (uint32_t)kc * A_BYTES) >> 4) & 0x3FFF), desc_hi | (uint64_t)(((sb0 + (uint32_t)kc * zb) >> 4) & 0x3FFF),
+                            idesc_z, kc > 0 ? 1u : 0u);
+          umma_chunk_commit_mask(tmem_d, desc_hi | (uint64_t)(((st0 + 3u * A_BYTES) >> 4) & 0x3FFF), desc_hi | (uint64_t)(((sb0 + 3u * zb) >> 4) & 0x3FFF), idesc_z, 1u,
+                                 4u, smem_u32(empty_bar + stage), all_mask);
+          if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
         } else {
-          for (int kc = 0; kc < 4; kc += 2) {
-            // o channels [0,128) come from G0's epilogue, [128,256) from G1's
-            mbar_wait_cluster(o_full + (kc >> 1), (uint32_t)it & 1);
+          // residual / skip: A = the o tile (channels [0,128) from G0's epilogue, [128,256) from G1's); final conv: A = relu(skip sum) in
+          // the staging tile (s_full)
+          const uint32_t a0 = kind == OP_FIN ? smem_u32(stg) : o0;
+          if (kind == OP_FIN) {
+            mbar_wait_cluster(su_full, (uint32_t)it & 1);
             tcgen05_fence_after();
-            L_TRACE(2 + (kc >> 1));
+          }
+          for (int kc = 0; kc < 4; kc += 2) {
+            if (kind != OP_FIN) {
+              mbar_wait_cluster(o_full + (kc >> 1), (uint32_t)it & 1);
+              tcgen05_fence_after();
+              L_TRACE(2 + (kc >> 1));
+            }
             mbar_wait(full_bar + stage, phase);
             tcgen05_fence_after();
-            const uint32_t sa = o0 + (uint32_t)kc * A_BYTES, sb = stage0 + (uint32_t)stage * L_STAGE_BYTES;
+            const uint32_t sa = a0 + (uint32_t)kc * A_BYTES, sb = stage0 + (uint32_t)stage * L_STAGE_BYTES;
             umma_chunk_pair(tmem_d, desc_hi | (uint64_t)((sa >> 4) & 0x3FFF), desc_hi | (uint64_t)((sb >> 4) & 0x3FFF), idesc, accumulate);
             umma_chunk_commit_mask(tmem_d, desc_hi | (uint64_t)(((sa + A_BYTES) >> 4) & 0x3FFF), desc_hi | (uint64_t)(((sb + A_BYTES) >> 4) & 0x3FFF),
                                    idesc, 1u, 4u, smem_u32(empty_bar + stage), all_mask);
@@ -353,8 +395,20 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
     // warp (which needs it for G1) without waiting for the skip MMAs to finish.
     uint4 held[4];
     int held_gk = -1;                             // op number of the K op the deferred store waits for, -1 = nothing held
+    double ls_sum = 0.0;                          // tail: sum of log_s over this thread's rows (forward direction)
     pdl_wait();
-    for_each_op(n_my, a.has_res != 0, [&](int it, int kind, int gop) {
+    // tail: the staging tile cycles  running skip sum (TMA) -> relu(skip sum) (K epilogue) -> relu(final) (F epilogue) -> free once the
+    // zero conv's MMAs have read it; the reload for the next tile is issued from here, by one thread, right after that point
+    auto load_skip_in = [&](int js) {
+      const int m_tile = 2 * (cl + js * ncl) + rank;
+      const int ub = m_tile / a.tiles_per_utt;
+      const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
+      mbar_expect_tx(stg_full, L_TILE_BYTES);
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) tma_load_3d(stg + (size_t)sub * A_BYTES, &a.mapIn, stg_full, sub * 64, t0, ub);
+    };
+    if (tail && warp == 2 && lane == 0 && n_my > 0) load_skip_in(0);
+    for_each_op(n_my, a.has_res != 0, tail, [&](int it, int kind, int gop) {
       const int m_tile = 2 * (cl + it * ncl) + rank;
       const int ub = m_tile / a.tiles_per_utt;
       const int t0 = (m_tile - ub * a.tiles_per_utt) * BM;
@@ -377,7 +431,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tmem_empty + slot, lead_cta);   // accumulator in registers: the MMA warp may reuse the half
-      if (held_gk >= 0) {   // deferred store of the previous G0 (see above): the last MMA that reads the old tile is K = op held_gk
+      if (held_gk >= 0 && kind != OP_ZERO) {   // deferred store of the previous G0 (see above): the last MMA that reads the old tile is K = op held_gk
         mbar_wait(tmem_full + (held_gk & 1), ((uint32_t)held_gk >> 1) & 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) sts128(o_u32 + tile_off(r, (cbeg + 16 * j) >> 1), held[j]);
@@ -428,7 +482,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
         if (kind == OP_G0 && it >= 1) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) held[j] = outv[j];
-          held_gk = gop + k_after_g0;
+          held_gk = gop + 1 + (a.has_res ? 1 : 0) + ((tail && it >= 2) ? 1 : 0);   // K(it-1): after [Z(it-2)] [R(it-1)]
         } else {
 #pragma unroll
           for (int j = 0; j < 64; j += 16) sts128(o_u32 + tile_off(r, (kind * 256 + cbeg + j) >> 1), outv[j >> 4]);
@@ -436,6 +490,85 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive_remote_release(o_full + kind, lead_cta);
         }
+      } else if (kind == OP_ZERO) {
+        // the zero conv's MMAs have completed (tmem_full): the staging tile is free -> fetch the next tile's running skip sum
+        if (warp == 2 && lane == 0 && it + 1 < n_my) load_skip_in(it + 1);
+        if (qtr == 0 && row_ok) {   // 4 warps: (log_s, t) pairs of this row = accumulator columns [0, Nz); ActNorm + coupling in place on x
+          const EpiArgs& e = a.ez;
+          float* xr = e.X + row * e.Cx;
+          const bool xfast = e.pairs_adjacent && e.Cx >= 16;
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            if (c0 >= a.Nz) break;
+            if (xfast) {   // pairs ordered by physical position: 16 columns = 16 consecutive floats of the row
+              const float4* bp = reinterpret_cast<const float4*>(e.an_b + c0);
+              const float4* sp = reinterpret_cast<const float4*>(e.an_s + c0);
+              const int bo = e.b_odd;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 b4 = __ldg(bp + k), s4 = __ldg(sp + k);
+                const float4 zb4 = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + 4 * k));
+                const float4 xq = *reinterpret_cast<const float4*>(xr + c0 + 4 * k);
+                float x[4] = {xq.x, xq.y, xq.z, xq.w};
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+                const float ac[4] = {__uint_as_float(v[c0 + 4 * k]) + zb4.x, __uint_as_float(v[c0 + 4 * k + 1]) + zb4.y,
+                                     __uint_as_float(v[c0 + 4 * k + 2]) + zb4.z, __uint_as_float(v[c0 + 4 * k + 3]) + zb4.w};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const float log_s = ac[2 * h], tt = ac[2 * h + 1];
+                  const int ib = 2 * h + bo, ia = 2 * h + 1 - bo;
+                  if (!e.reverse) {
+                    x[ia] = (x[ia] + bb[ia]) * ss[ia];
+                    x[ib] = ((x[ib] + bb[ib]) * ss[ib] - tt) * __expf(-log_s);
+                    ls_sum += (double)log_s;
+                  } else {
+                    x[ib] = (x[ib] * __expf(log_s) + tt) * ss[ib] - bb[ib];
+                    x[ia] = x[ia] * ss[ia] - bb[ia];
+                  }
+                }
+                *reinterpret_cast<float4*>(xr + c0 + 4 * k) = make_float4(x[0], x[1], x[2], x[3]);
+              }
+            } else {
+#pragma unroll
+              for (int p = 0; p < 8; ++p) {
+                const int q = c0 / 2 + p;
+                if (q >= e.nq) break;
+                const float log_s = __uint_as_float(v[c0 + 2 * p]) + __ldg(e.bias + c0 + 2 * p);
+                const float tt = __uint_as_float(v[c0 + 2 * p + 1]) + __ldg(e.bias + c0 + 2 * p + 1);
+                const int oa = __ldg(e.a_off + q), ob = __ldg(e.b_off + q);
+                float xa = xr[oa], xb = xr[ob];
+                if (!e.reverse) {
+                  xa = (xa + __ldg(e.an_b + oa)) * __ldg(e.an_s + oa);
+                  xb = (xb + __ldg(e.an_b + ob)) * __ldg(e.an_s + ob);
+                  xb = (xb - tt) * __expf(-log_s);
+                  ls_sum += (double)log_s;
+                } else {
+                  xb = xb * __expf(log_s) + tt;
+                  xa = xa * __ldg(e.an_s + oa) - __ldg(e.an_b + oa);
+                  xb = xb * __ldg(e.an_s + ob) - __ldg(e.an_b + ob);
+                }
+                xr[oa] = xa;
+                xr[ob] = xb;
+              }
+            }
+          }
+        }
+      } else if (kind == OP_FIN) {
+        // relu(final conv) over this thread's 64 columns, in place over relu(skip sum) in the staging tile (the final conv's MMAs have
+        // completed: tmem_full) -- the A operand of the zero conv
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.final_bias + cbeg + 8 * k));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.final_bias + cbeg + 8 * k + 4));
+          const uint32_t p0 = pack16(fmaxf(__uint_as_float(v[8 * k]) + b0.x, 0.f), fmaxf(__uint_as_float(v[8 * k + 1]) + b0.y, 0.f), fp16);
+          const uint32_t p1 = pack16(fmaxf(__uint_as_float(v[8 * k + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[8 * k + 3]) + b0.w, 0.f), fp16);
+          const uint32_t p2 = pack16(fmaxf(__uint_as_float(v[8 * k + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[8 * k + 5]) + b1.y, 0.f), fp16);
+          const uint32_t p3 = pack16(fmaxf(__uint_as_float(v[8 * k + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[8 * k + 7]) + b1.w, 0.f), fp16);
+          sts128(stg_u32 + tile_off(r, cbeg + 8 * k), make_uint4(p0, p1, p2, p3));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_release(su_full + 1, lead_cta);
       } else {
         const bool is_res = kind == OP_RES;
         const float* bias = a.rs_bias + ((!is_res && a.has_res) ? 256 : 0) + cbeg;
@@ -485,7 +618,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        if (tail) {   // relu(skip sum) stays in the staging tile: the A operand of the final conv
+          if (lane == 0) mbar_arrive_remote_release(su_full, lead_cta);
+        } else if (lane == 0) {
           // this warp's 32 rows x 64 columns leave as one TMA store (rows >= Ti and the dummy tile of an odd pair are clipped)
           if (!(a.dbg & 1))
             tma_store_3d(is_res ? &a.mapOutH : &a.mapOutS, stg + (size_t)qtr * A_BYTES + (size_t)lg * 32 * 128, qtr * 64, t0 + lg * 32, ub);
@@ -502,6 +637,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) layer_kernel(const __grid_consta
       if (warp == 2) L_TRACE(7);
     });
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tail && qtr == 0 && !a.ez.reverse && a.ez.logdet_acc) {
+      ls_sum = warp_sum(ls_sum);
+      if (lane == 0 && ls_sum != 0.0) atomicAdd(a.ez.logdet_acc, ls_sum);
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -525,7 +664,7 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
   if (trace_state < 0) {
     const char* e = getenv("FWN_LAYER_TRACE");
     trace_state = (e && e[0] == '1') ? 1 : 0;
-    if (trace_state == 1) FWN_CUDA(cudaMalloc(&trace_buf, (L_TRACE_TILES * 4 * L_TRACE_K + L_TRACE_TILES) * sizeof(long long)));
+    if (trace_state == 1) FWN_CUDA(cudaMalloc(&trace_buf, (L_TRACE_TILES * 6 * L_TRACE_K + L_TRACE_TILES) * sizeof(long long)));
   }
   static int printed[2] = {0, 0};   // one residual layer and one last layer
   static int trace_skip = -1, seen[2] = {0, 0};
@@ -536,7 +675,7 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
   bool tracing = trace_state == 1 && a.B * a.tiles_per_utt >= 8000 && !printed[a.has_res ? 1 : 0];
   if (tracing && seen[a.has_res ? 1 : 0]++ < trace_skip) tracing = false;
   if (tracing) {
-    FWN_CUDA(cudaMemsetAsync(trace_buf, 0, (L_TRACE_TILES * 4 * L_TRACE_K + L_TRACE_TILES) * sizeof(long long), st));
+    FWN_CUDA(cudaMemsetAsync(trace_buf, 0, (L_TRACE_TILES * 6 * L_TRACE_K + L_TRACE_TILES) * sizeof(long long), st));
     a.trace = trace_buf;
   }
   static bool configured = false;
@@ -569,13 +708,13 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
   FWN_CUDA(cudaLaunchKernelEx(&cfg, layer_kernel, a));
   FWN_LAUNCH_CHECK();
   if (tracing) {   // diagnostics only (run with FWN_GRAPH=0): timeline of the first tiles of cluster 0, cycles relative to the first event
-    long long h[L_TRACE_TILES * 4 * L_TRACE_K + L_TRACE_TILES];
+    long long h[L_TRACE_TILES * 6 * L_TRACE_K + L_TRACE_TILES];
     FWN_CUDA(cudaStreamSynchronize(st));
     FWN_CUDA(cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost));
     const long long t00 = h[0];
     {
-      const long long* gt = h + L_TRACE_TILES * 4 * L_TRACE_K;
-      const double cyc = (double)(h[((L_TRACE_TILES - 1) * 4 + OP_G0) * L_TRACE_K + 1] - h[OP_G0 * L_TRACE_K + 1]);
+      const long long* gt = h + L_TRACE_TILES * 6 * L_TRACE_K;
+      const double cyc = (double)(h[((L_TRACE_TILES - 1) * 6 + OP_G0) * L_TRACE_K + 1] - h[OP_G0 * L_TRACE_K + 1]);
       const double ns = (double)(gt[L_TRACE_TILES - 1] - gt[0]);
       fprintf(stderr, "layer trace: tiles %d..%d of cluster 0: %.0f cycles in %.0f ns = %.3f GHz, %.0f cycles / %.2f us per tile\n", L_TRACE_T0,
               L_TRACE_T0 + L_TRACE_TILES - 1, cyc, ns, cyc / ns, cyc / (L_TRACE_TILES - 1), ns / (L_TRACE_TILES - 1) * 1e-3);
@@ -583,11 +722,11 @@ int launch_layer(const LayerArgs& a0, cudaStream_t st) {
     fprintf(stderr, "layer trace: has_res=%d nseg=%d chunks=%d+%d+%d+%d  [mma: wait_tmem_empty, go, o_lo, o_hi, issued | epi: wait_full, full, done]\n", a.has_res,
             a.nseg, a.nchunk[0], a.nchunk[1], a.nchunk[2], a.nchunk[3]);
     for (int it = 0; it < L_TRACE_TILES; ++it)
-      for (int opi = 0; opi < 4; ++opi) {
-        if (opi == 2 && !a.has_res) continue;
+      for (int opi = 0; opi < 6; ++opi) {
+        if ((opi == 2 && !a.has_res) || (opi >= 4 && !a.tail)) continue;
         fprintf(stderr, "  tile %d op %d:", it, opi);
         for (int k = 0; k < L_TRACE_K; ++k) {
-          const long long v = h[(it * 4 + opi) * L_TRACE_K + k];
+          const long long v = h[(it * 6 + opi) * L_TRACE_K + k];
           fprintf(stderr, " %8lld", v ? v - t00 : -1);
         }
         fprintf(stderr, "\n");

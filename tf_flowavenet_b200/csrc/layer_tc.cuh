@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernels.h"
+
 namespace fwn {
 namespace tc {
 
@@ -23,6 +25,14 @@ struct alignas(64) LayerArgs {
   int B, Ti, tiles_per_utt;
   const float* gate_bias;  // [2F] (filter, gate) interleaved
   const float* rs_bias;    // [2F] or [F]
+  // last layer only: the WaveNet tail in the same launch -- relu(skip sum) stays in the staging tile as the A operand of the final 1x1,
+  // relu(final) replaces it in place as the A operand of the zero conv, whose epilogue is ActNorm + affine coupling on x
+  int tail;                // 1: ops F (final conv) and Z (zero conv + affine) follow every tile's skip op; nothing is stored by the skip op
+  CUtensorMap mapWf;       // final-conv weights [F][F] K-major, (64, 128) boxes
+  CUtensorMap mapWz;       // zero-conv weights [Npad][F] K-major, (64, NzBox / 2) boxes (one CTA's half of the second MMA's B operand)
+  int Nz, NzBox;           // 2 nq (log_s, t) columns; N of the zero-conv MMA (16 or 32)
+  const float* final_bias; // [F]
+  EpiArgs ez;              // the affine epilogue's arguments (bias = zero-conv bias)
   const float* pc;         // deep blocks: this layer's slice of the conditioning projection computed ahead, fp32 [rows, pc_ld]; else null
   int64_t pc_ld;
   int dbg;                 // diagnostics (FWN_LAYER_DBG bitmask): 1 no 1x1 TMA stores, 2 no staging loads, 4 no 1x1 epilogue math, 8 no activation loads for the second gate half, 16 no L2 prefetch (1..8: WRONG results)

@@ -884,6 +884,15 @@ static int64_t layer_fusion_min_pairs() {
   }
   return v;
 }
+// FWN_LAYER_TAIL=0 keeps the tail out of the last layer's fused launch (it then runs as the separate tail kernel)
+static bool layer_tail_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FWN_LAYER_TAIL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static bool fp32_front_on_tensor_cores() {
   static int v = -1;
   if (v < 0) {
@@ -948,6 +957,31 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
   }
   prof_end(m, st);
 
+  // the WaveNet tail (final 1x1 + ReLU, zero conv + ActNorm / affine coupling): described here because the last layer's fused launch
+  // can carry it (layer_tc.cu, tail ops)
+  GemmArgs tf_ = {};
+  tf_.B = B; tf_.Ti = Ti;
+  tf_.seg[0] = Seg{w.s, F, 0, F, 0};
+  tf_.nseg = 1;
+  tf_.W = fp.final_w; tf_.ldw = fp.final_ld; tf_.N = F;
+  tf_.e.bias = fp.final_b; tf_.e.out0 = w.u; tf_.e.ld = F; tf_.e.relu = 1; tf_.e.F = F;
+  GemmArgs tz_ = {};
+  tz_.B = B; tz_.Ti = Ti;
+  tz_.seg[0] = Seg{w.u, F, 0, F, 0};
+  tz_.nseg = 1;
+  tz_.W = fp.zero_w; tz_.ldw = fp.zero_ld; tz_.N = 2 * fp.nq;
+  tz_.e.bias = fp.zero_b; tz_.e.F = F;
+  tz_.e.X = X; tz_.e.Cx = fp.Cx; tz_.e.nq = fp.nq; tz_.e.a_off = fp.a_off; tz_.e.b_off = fp.b_off;
+  tz_.e.an_b = fp.an_b; tz_.e.an_s = reverse ? fp.an_is : fp.an_s;
+  tz_.e.logdet_acc = reverse ? nullptr : w.sums;
+  tz_.e.reverse = reverse;
+  tz_.e.pairs_adjacent = fp.pairs_adjacent;
+  tz_.e.b_odd = fp.b_odd;
+  const double final_flop = 2.0 * rows * F * F, zero_flop = 2.0 * rows * F * (c.affine ? fp.Cx : fp.nq);
+  const bool fuse_tail = m->fuse_layer < 0 ? tail_fusion_enabled() : m->fuse_layer != 0;
+  const bool tail_ok = bf16 && fuse_tail && tc_tail_supported(m, tf_, tz_);
+  bool tail_done = false;
+
   void* hin = w.h0;
   void* hout = w.h1;
   const void* cond = fp.cond_half == 0 ? w.cA : w.cB;
@@ -980,11 +1014,14 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     const int64_t row_pairs = ((int64_t)B * ((Ti + 127) / 128) + 1) / 2;
     const bool fuse = m->fuse_layer < 0 ? (layer_fusion_enabled() && row_pairs >= layer_fusion_min_pairs()) : m->fuse_layer != 0;
     if (bf16 && fuse && tc_layer_supported(m, g, r)) {
-      // gate GEMM -> tanh*sigmoid -> res|skip 1x1 in one launch: o stays in shared memory (layer_tc.cu)
-      prof_begin(m, PROF_GATE, gate_flop + rs_flop, st);
+      // gate GEMM -> tanh*sigmoid -> res|skip 1x1 in one launch: o stays in shared memory (layer_tc.cu); the last layer's launch
+      // also carries the tail (relu(skip sum) and relu(final) stay in shared memory too) when it has a running skip sum to stage
+      const bool with_tail = last && tail_ok && n > 0 && layer_tail_enabled();
+      prof_begin(m, PROF_GATE, gate_flop + rs_flop + (with_tail ? final_flop + zero_flop : 0.0), st);
       m->launches++;
-      if (tc_run_layer(m, g, r, n, fp, st)) return 1;
+      if (tc_run_layer(m, g, r, n, fp, st, with_tail ? &tf_ : nullptr, with_tail ? &tz_ : nullptr)) return 1;
       prof_end(m, st);
+      tail_done = with_tail;
     } else {
       prof_begin(m, PROF_GATE, gate_flop, st);
       if (run_gemm(m, g, EPI_GATE, GEMM_GATE0 + n, fp, st)) return 1;
@@ -995,41 +1032,20 @@ static int run_flow(Model* m, const Workspace& w, const FlowPack& fp, float* X, 
     }
     std::swap(hin, hout);
   }
-  {
-    GemmArgs g = {};
-    g.B = B; g.Ti = Ti;
-    g.seg[0] = Seg{w.s, F, 0, F, 0};
-    g.nseg = 1;
-    g.W = fp.final_w; g.ldw = fp.final_ld; g.N = F;
-    g.e.bias = fp.final_b; g.e.out0 = w.u; g.e.ld = F; g.e.relu = 1; g.e.F = F;
-    GemmArgs z = {};
-    z.B = B; z.Ti = Ti;
-    z.seg[0] = Seg{w.u, F, 0, F, 0};
-    z.nseg = 1;
-    z.W = fp.zero_w; z.ldw = fp.zero_ld; z.N = 2 * fp.nq;
-    z.e.bias = fp.zero_b; z.e.F = F;
-    z.e.X = X; z.e.Cx = fp.Cx; z.e.nq = fp.nq; z.e.a_off = fp.a_off; z.e.b_off = fp.b_off;
-    z.e.an_b = fp.an_b; z.e.an_s = reverse ? fp.an_is : fp.an_s;
-    z.e.logdet_acc = reverse ? nullptr : w.sums;
-    z.e.reverse = reverse;
-    z.e.pairs_adjacent = fp.pairs_adjacent;
-    z.e.b_odd = fp.b_odd;
-    const double final_flop = 2.0 * rows * F * F, zero_flop = 2.0 * rows * F * (c.affine ? fp.Cx : fp.nq);
-    const bool fuse_tail = m->fuse_layer < 0 ? tail_fusion_enabled() : m->fuse_layer != 0;
-    if (bf16 && fuse_tail && tc_tail_supported(m, g, z)) {
-      // final 1x1 + ReLU -> zero conv -> ActNorm / affine coupling on x in one launch: u stays in shared memory (tail_tc.cu)
-      prof_begin(m, PROF_FINAL, final_flop + zero_flop, st);
-      m->launches++;
-      if (tc_run_tail(m, g, z, fp, st)) return 1;
-      prof_end(m, st);
-    } else {
-      prof_begin(m, PROF_FINAL, final_flop, st);
-      if (run_gemm(m, g, EPI_PLAIN, GEMM_FINAL, fp, st)) return 1;
-      prof_end(m, st);
-      prof_begin(m, PROF_ZERO_AFFINE, zero_flop, st);
-      if (run_gemm(m, z, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
-      prof_end(m, st);
-    }
+  if (tail_done) return 0;
+  if (tail_ok) {
+    // final 1x1 + ReLU -> zero conv -> ActNorm / affine coupling on x in one launch: u stays in shared memory (tail_tc.cu)
+    prof_begin(m, PROF_FINAL, final_flop + zero_flop, st);
+    m->launches++;
+    if (tc_run_tail(m, tf_, tz_, fp, st)) return 1;
+    prof_end(m, st);
+  } else {
+    prof_begin(m, PROF_FINAL, final_flop, st);
+    if (run_gemm(m, tf_, EPI_PLAIN, GEMM_FINAL, fp, st)) return 1;
+    prof_end(m, st);
+    prof_begin(m, PROF_ZERO_AFFINE, zero_flop, st);
+    if (run_gemm(m, tz_, EPI_AFFINE, GEMM_ZERO, fp, st)) return 1;
+    prof_end(m, st);
   }
   return 0;
 }

@@ -156,7 +156,8 @@ void engine_free(Model* m);
 // fused ResBlock layer on the tcgen05 engine (gemm_tc.cu / layer_tc.cu): gate GEMM `g` + res|skip 1x1 `r` of layer `layer`
 bool tc_layer_supported(const Model* m, const GemmArgs& g, const GemmArgs& r);
 int train_ensure_full_planes(Model* m, cudaStream_t st);   // train.cu
-int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st);
+int tc_run_layer(Model* m, const GemmArgs& g, const GemmArgs& r, int layer, const FlowPack& fp, cudaStream_t st, const GemmArgs* fin = nullptr,
+                 const GemmArgs* zero = nullptr);   // fin, zero: fold the WaveNet tail into the last layer's launch
 // fused WaveNet tail (gemm_tc.cu / tail_tc.cu): final 1x1 `f` + zero conv / affine coupling `z`
 bool tc_tail_supported(const Model* m, const GemmArgs& f, const GemmArgs& z);
 int tc_run_tail(Model* m, const GemmArgs& f, const GemmArgs& z, const FlowPack& fp, cudaStream_t st);
