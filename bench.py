@@ -455,9 +455,10 @@ def run_pass(args, dist, workload, with_cpu=True, steps=None):
                              "unit": "GB/s" if k == "upsample" else "TFLOP/s"} for k, v in prof.items()},
             "whole_pass_tflops": value * MFLOP_PER_SAMPLE[preset] * 1e6 / 1e12 / world}
     if fused:
-        roof["note"] = ("gate_gemm family = the fused layer kernel (gate + res|skip FLOPs, HBM-side epilogue I/O included); final_conv family = the "
-                        "fused tail kernel (final 1x1 + zero conv + affine).  With the 1x1 epilogue I/O switched off the layer kernel runs at the "
-                        "power-capped tensor rate (profiles/r2_ncu_fused.md)")
+        roof["note"] = ("gate_gemm family = the fused layer kernel (gate + res|skip FLOPs, HBM-side epilogue I/O included; the last layer's launch "
+                        "also carries the WaveNet tail = final 1x1 + zero conv + affine, whose FLOPs are counted here); final_conv family = the "
+                        "separate fused tail kernel where the last layer is not fused.  With the 1x1 epilogue I/O switched off the layer kernel "
+                        "runs at the power-capped tensor rate (profiles/r2_ncu_fused.md)")
     tp = os.path.join(ROOT, "profiles", "r2_layer_traffic.json" if fused else "r1_gate_traffic.json")
     if mixed and workload == "c3" and os.path.exists(tp):
         tj = json.load(open(tp))

@@ -140,8 +140,8 @@ int fwn_apply_gradients(fwn_handle h, const float* grads, float lr, float beta1,
  * that are small differences of large sums then carry errors up to ~1e-3 of the model's largest gradient entry). */
 int fwn_set_split_terms(fwn_handle h, int inference_terms, int training_terms);
 /* Mixed-precision passes: how the coupling WaveNet (modules.py:113-128, 161-186) is launched.  1 = fused kernels: one per ResBlock
- * layer (gate GEMM -> tanh*sigmoid -> res|skip 1x1, the gated tile kept in shared memory) and one for the tail (final 1x1 + ReLU ->
- * ZeroConv1d -> ActNorm / affine coupling on x); 0 = one launch per GEMM with the intermediate activations round-tripping through
+ * layer (gate GEMM -> tanh*sigmoid -> res|skip 1x1, the gated tile kept in shared memory), the last layer's launch also carrying the tail
+ * (final 1x1 + ReLU -> ZeroConv1d -> ActNorm / affine coupling on x; a separate tail kernel where the layer is not fused); 0 = one launch per GEMM with the intermediate activations round-tripping through
  * HBM; -1 = default (fused where it pays: large launches for the layer kernel; FWN_FUSE_LAYER=0 / FWN_FUSE_TAIL=0 disable).
  * The layer kernel is bit-identical to its two launches; the tail kernel rounds the same 16-bit u. */
 int fwn_set_layer_fusion(fwn_handle h, int mode);
