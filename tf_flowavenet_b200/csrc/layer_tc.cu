@@ -20,7 +20,11 @@
 // Shared memory (227 KB): 3 pipeline stages x (16 KB A + 16 KB weight half-box) | o tile 64 KB | staging tile 64 KB | gate bias.
 // The 1x1 ops pack two weight K chunks into one stage.  The staging tile carries their in-place epilogue I/O: TMA loads h_in (or the
 // running skip sum) one gate half ahead, the residual op updates each warp's 32 x 64 region in place and TMA-stores h_out, then the
-// skip op reuses the region for the skip tile.  Measurements, timelines and the rejected variants: profiles/r2_ncu_fused.md.
+// skip op reuses the region for the skip tile.
+// Last layer with LayerArgs::tail: the WaveNet tail rides in the same launch as two more op kinds -- F (final 1x1 on relu(skip sum), which
+// the skip op leaves in the staging tile instead of storing it) and Z (zero conv on relu(final), written in place over it; epilogue =
+// ActNorm + affine coupling on x, model.py:7-105,121-161) -- see for_each_op for the program.  Neither the skip sum nor u reaches HBM.
+// Measurements, timelines and the rejected variants: profiles/r2_ncu_fused.md.
 #include <cuda.h>
 #include <stdio.h>
 
